@@ -1,0 +1,129 @@
+// conv_api.cu — C-ABI dispatch for Conv2d / ConvTranspose2d forward, data gradient and weight gradient.
+// Maps (operation, transposed) onto the two gather-GEMM modes and picks the engine (tcgen05 or generic).
+// Replaces nn.Conv2d / nn.ConvTranspose2d + autograd (models/networks.py:350,357,369-372,376,426,439,576,
+// 583,591,597; models/stn/layers.py:85).
+#include "common.cuh"
+#include "conv_internal.cuh"
+
+static bool geom_ok(const nemar_conv_geom* g) {
+  return g && g->cin > 0 && g->cout > 0 && g->kh > 0 && g->kw > 0 && g->stride > 0 && g->pad >= 0 &&
+         g->kh == g->kw;
+}
+
+NEMAR_API int nemar_pack_weights(const float* w, const nemar_conv_geom* g, int dtype, int cin_p, int cout_p,
+                                 void* wf, void* wd, void* stream) {
+  NEMAR_REQUIRE(w && geom_ok(g) && cin_p >= g->cin && cout_p >= g->cout, "pack_weights: bad args");
+  cudaStream_t s = (cudaStream_t)stream;
+  int rc = 0;
+  if (!g->transposed) {
+    // w[cout][cin][kh][kw]
+    if (wf) rc = generic_pack(w, wf, dtype, g->cout, g->cin, cin_p, g->kh, g->kw, /*w_is_oi=*/1, /*flip=*/0, s);
+    if (!rc && wd) rc = generic_pack(w, wd, dtype, g->cin, g->cout, cout_p, g->kh, g->kw, /*w_is_oi=*/0, /*flip=*/1, s);
+  } else {
+    // w[cin][cout][kh][kw]; forward pack [cout][taps][cin_p] flipped, backward pack [cin][taps][cout_p]
+    if (wf) rc = generic_pack(w, wf, dtype, g->cout, g->cin, cin_p, g->kh, g->kw, /*w_is_oi=*/0, /*flip=*/1, s);
+    if (!rc && wd) rc = generic_pack(w, wd, dtype, g->cin, g->cout, cout_p, g->kh, g->kw, /*w_is_oi=*/1, /*flip=*/0, s);
+  }
+  return rc;
+}
+
+static int expected_out(int in, const nemar_conv_geom* g) {
+  return (in + 2 * g->pad - g->kh) / g->stride + 1;
+}
+
+NEMAR_API int nemar_conv2d_fprop(const nemar_tensor* x, const void* w_packed, int w_cin_p, const float* bias,
+                                 const nemar_conv_geom* g, int act, const nemar_tensor* y, float* stats,
+                                 int use_tc, void* stream) {
+  NEMAR_REQUIRE(view_ok(x) && view_ok(y) && w_packed && geom_ok(g), "conv2d_fprop: bad args");
+  NEMAR_REQUIRE(x->c == g->cin && y->c == g->cout && x->n == y->n && w_cin_p >= g->cin &&
+                    (x->dtype == y->dtype || (!use_tc && y->dtype == NEMAR_F32)),
+                "conv2d_fprop: channel/dtype mismatch (weights share x's dtype; y may be fp32 on the generic engine)");
+  NEMAR_REQUIRE(y->pad == 0, "conv2d_fprop: output must not carry a halo");
+  cudaStream_t s = (cudaStream_t)stream;
+  GatherGeom gg;
+  gg.kh = g->kh; gg.kw = g->kw; gg.dst_padded = 0;
+  if (!g->transposed) {
+    NEMAR_REQUIRE(x->pad <= g->pad, "conv2d_fprop: input halo larger than the conv padding");
+    NEMAR_REQUIRE(y->h == expected_out(x->h, g) && y->w == expected_out(x->w, g), "conv2d_fprop: bad output extent");
+    gg.sm = g->stride; gg.sd = 1; gg.pe = g->pad - x->pad;
+  } else {
+    NEMAR_REQUIRE(x->pad == 0, "conv2d_fprop(transposed): input halo not supported");
+    int lo_h = (x->h - 1) * g->stride - 2 * g->pad + g->kh, lo_w = (x->w - 1) * g->stride - 2 * g->pad + g->kw;
+    NEMAR_REQUIRE(y->h >= lo_h && y->h < lo_h + g->stride && y->w >= lo_w && y->w < lo_w + g->stride,
+                  "conv2d_fprop(transposed): bad output extent");
+    gg.sm = 1; gg.sd = g->stride; gg.pe = g->kh - 1 - g->pad;
+  }
+  int rc;
+  if (use_tc) {
+    NEMAR_REQUIRE(tc_gather_supported(x, y, w_cin_p, gg), "conv2d_fprop: geometry not supported by the tcgen05 engine");
+    rc = tc_gather_gemm(x, y, w_packed, w_cin_p, bias, act, stats, gg, s);
+  } else {
+    rc = generic_gather_gemm(x, y, w_packed, x->dtype, w_cin_p, bias, act, gg, s);
+    if (!rc && stats) {
+      NEMAR_REQUIRE(act == NEMAR_ACT_NONE, "conv2d_fprop: stats need the pre-activation output");
+      rc = nemar_instnorm_stats(y, stats, stream);
+    }
+  }
+  return rc;
+}
+
+NEMAR_API int nemar_conv2d_dgrad(const nemar_tensor* dy, const void* w_packed_d, int w_cout_p,
+                                 const nemar_conv_geom* g, const nemar_tensor* dx, int use_tc, void* stream) {
+  NEMAR_REQUIRE(view_ok(dy) && view_ok(dx) && w_packed_d && geom_ok(g), "conv2d_dgrad: bad args");
+  NEMAR_REQUIRE(dy->c == g->cout && dx->c == g->cin && dx->n == dy->n && w_cout_p >= g->cout && dy->pad == 0 &&
+                    (dx->dtype == dy->dtype || (!use_tc && dy->dtype == NEMAR_F32)),
+                "conv2d_dgrad: channel/dtype mismatch (weights share dx's dtype; dy may be fp32 on the generic engine)");
+  cudaStream_t s = (cudaStream_t)stream;
+  GatherGeom gg;
+  gg.kh = g->kh; gg.kw = g->kw;
+  if (!g->transposed) {
+    NEMAR_REQUIRE(dx->pad <= g->pad, "conv2d_dgrad: dx halo larger than the conv padding");
+    gg.sm = 1; gg.sd = g->stride; gg.pe = g->kh - 1 - (g->pad - dx->pad); gg.dst_padded = dx->pad > 0;
+  } else {
+    NEMAR_REQUIRE(dx->pad == 0, "conv2d_dgrad(transposed): halo not supported");
+    gg.sm = g->stride; gg.sd = 1; gg.pe = g->pad; gg.dst_padded = 0;
+  }
+  if (use_tc) {
+    NEMAR_REQUIRE(tc_gather_supported(dy, dx, w_cout_p, gg), "conv2d_dgrad: geometry not supported by the tcgen05 engine");
+    return tc_gather_gemm(dy, dx, w_packed_d, w_cout_p, nullptr, NEMAR_ACT_NONE, nullptr, gg, s);
+  }
+  return generic_gather_gemm(dy, dx, w_packed_d, dx->dtype, w_cout_p, nullptr, NEMAR_ACT_NONE, gg, s);
+}
+
+// conv-view of a weight-gradient problem: for ConvTranspose2d the roles of x and dy swap.
+static void wgrad_view(const nemar_tensor* x, const nemar_tensor* dy, const nemar_conv_geom* g,
+                       const nemar_tensor** xc, const nemar_tensor** dyc, int* pe) {
+  if (!g->transposed) { *xc = x; *dyc = dy; *pe = g->pad - x->pad; }
+  else { *xc = dy; *dyc = x; *pe = g->pad - dy->pad; }
+}
+
+NEMAR_API int64_t nemar_conv2d_wgrad_workspace(const nemar_tensor* x, const nemar_tensor* dy,
+                                               const nemar_conv_geom* g, int use_tc) {
+  if (!use_tc || !view_ok(x) || !view_ok(dy) || !geom_ok(g)) return 0;
+  const nemar_tensor *xc, *dyc; int pe;
+  wgrad_view(x, dy, g, &xc, &dyc, &pe);
+  return tc_wgrad_workspace(xc, dyc, g->kh, g->kw, g->stride, pe);
+}
+
+NEMAR_API int nemar_conv2d_wgrad(const nemar_tensor* x, const nemar_tensor* dy, const nemar_conv_geom* g,
+                                 float* dw, void* workspace, int64_t workspace_bytes, int use_tc, void* stream) {
+  NEMAR_REQUIRE(view_ok(x) && view_ok(dy) && dw && geom_ok(g), "conv2d_wgrad: bad args");
+  NEMAR_REQUIRE(x->c == g->cin && dy->c == g->cout && x->n == dy->n && (x->dtype == dy->dtype || !use_tc),
+                "conv2d_wgrad: channel/dtype mismatch");
+  const nemar_tensor *xc, *dyc; int pe;
+  wgrad_view(x, dy, g, &xc, &dyc, &pe);
+  NEMAR_REQUIRE(dyc->pad == 0 && pe >= 0, "conv2d_wgrad: unsupported halo configuration");
+  cudaStream_t s = (cudaStream_t)stream;
+  if (use_tc) {
+    NEMAR_REQUIRE(tc_wgrad_supported(xc, dyc, g->kh, g->kw, g->stride, pe),
+                  "conv2d_wgrad: geometry not supported by the tcgen05 engine");
+    return tc_wgrad(xc, dyc, dw, g->kh, g->kw, g->stride, pe, workspace, workspace_bytes, s);
+  }
+  return generic_wgrad(xc, dyc, dw, g->kh, g->kw, g->stride, pe, s);
+}
+
+NEMAR_API int nemar_conv2d_tc_supported(const nemar_conv_geom* g, int dtype, int h_in, int w_in) {
+  (void)h_in; (void)w_in;
+  if (!geom_ok(g) || dtype != NEMAR_BF16) return 0;
+  return (g->cin % 64 == 0 && g->cout % 64 == 0) ? 1 : 0;
+}
