@@ -1,0 +1,26 @@
+"""Engine-wide settings (set once from the command line, read by every layer)."""
+import torch
+
+
+class EngineConfig:
+    def __init__(self):
+        self.precision = "bf16"      # storage dtype of activations / packed weights: "bf16" | "fp32"
+        self.conv_engine = "auto"    # "auto": tcgen05 where supported, else generic; "generic": CUDA cores only
+        self.dropout_seed = 0x5EED
+
+    @property
+    def dtype(self):
+        return torch.bfloat16 if self.precision == "bf16" else torch.float32
+
+
+CONFIG = EngineConfig()
+
+
+def configure(precision=None, conv_engine=None):
+    if precision is not None:
+        assert precision in ("bf16", "fp32")
+        CONFIG.precision = precision
+    if conv_engine is not None:
+        assert conv_engine in ("auto", "generic")
+        CONFIG.conv_engine = conv_engine
+    return CONFIG

@@ -1,0 +1,548 @@
+"""Autograd bindings: every differentiable op of the hot path as a torch.autograd.Function whose forward
+and backward are single calls into libnemar_b200.so.  PyTorch supplies device memory, streams and the
+autograd tape only — no ATen compute kernel runs on the named ops.
+
+Engine tensors are contiguous [N, H+2*pad, W+2*pad, C] (channels innermost); the halo size is static
+architecture knowledge passed alongside.  Images crossing the reference-facing boundary are NCHW fp32.
+"""
+import torch
+from torch.autograd import Function
+
+from . import lib as L
+from .lib import call, fptr, i64, stream, view, vptr
+
+_weights_epoch = [0]
+
+
+def bump_weights_epoch():
+    """Invalidate packed-weight caches (called by the optimizer step and by load_state_dict)."""
+    _weights_epoch[0] += 1
+
+
+def weights_epoch():
+    return _weights_epoch[0]
+
+
+def _c(t):
+    return t if t.is_contiguous() else t.contiguous()
+
+
+# ------------------------------------------------------------------------------------------------
+# layout crossings
+# ------------------------------------------------------------------------------------------------
+class ImagesToNHWC(Function):
+    """cat(NCHW fp32 images, dim=1) -> engine tensor with optional reflect/zero halo and channel padding."""
+
+    @staticmethod
+    def forward(ctx, pad, pad_mode, dtype, cp, *imgs):
+        imgs = [_c(i) for i in imgs]
+        n, _, h, w = imgs[0].shape
+        chans = [int(i.shape[1]) for i in imgs]
+        ctot = sum(chans)
+        cp = max(cp, ctot)
+        out = torch.empty((n, h + 2 * pad, w + 2 * pad, cp), dtype=dtype, device=imgs[0].device)
+        if cp > ctot:
+            call("nemar_fill_channels", view(out, pad), ctot, cp - ctot, stream())
+        coff = 0
+        for img, c in zip(imgs, chans):
+            assert img.dtype == torch.float32 and img.shape[0] == n and img.shape[2] == h and img.shape[3] == w
+            call("nemar_nchw_to_nhwc", fptr(img), view(out, pad, coff, c), pad_mode, stream())
+            coff += c
+        ctx.meta = (pad, pad_mode, chans, (n, h, w))
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        pad, pad_mode, chans, (n, h, w) = ctx.meta
+        g = _c(g)
+        grads, coff = [], 0
+        for k, c in enumerate(chans):
+            if ctx.needs_input_grad[4 + k]:
+                d = torch.empty((n, c, h, w), dtype=torch.float32, device=g.device)
+                call("nemar_nhwc_to_nchw", view(g, pad, coff, c), fptr(d), pad_mode, 0, stream())
+                grads.append(d)
+            else:
+                grads.append(None)
+            coff += c
+        return (None, None, None, None, *grads)
+
+
+class ToNCHW(Function):
+    """engine tensor (first c channels) -> NCHW fp32 image."""
+
+    @staticmethod
+    def forward(ctx, x, c):
+        x = _c(x)
+        n, h, w, cs = x.shape
+        out = torch.empty((n, c, h, w), dtype=torch.float32, device=x.device)
+        call("nemar_nhwc_to_nchw", view(x, 0, 0, c), fptr(out), L.PAD_ZERO, 0, stream())
+        ctx.meta = (x.shape, x.dtype, c)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        shape, dtype, c = ctx.meta
+        g = _c(g)
+        dx = torch.empty(shape, dtype=dtype, device=g.device)
+        if shape[3] > c:
+            call("nemar_fill_channels", view(dx), c, shape[3] - c, stream())
+        call("nemar_nchw_to_nhwc", fptr(g), view(dx, 0, 0, c), L.PAD_ZERO, stream())
+        return dx, None
+
+
+class Concat(Function):
+    """channel concat of two engine tensors (unet_stn.py:97)."""
+
+    @staticmethod
+    def forward(ctx, a, b):
+        a, b = _c(a), _c(b)
+        n, h, w, ca = a.shape
+        cb = b.shape[3]
+        out = torch.empty((n, h, w, ca + cb), dtype=a.dtype, device=a.device)
+        call("nemar_copy_view", view(a), view(out, 0, 0, ca), L.PAD_ZERO, stream())
+        call("nemar_copy_view", view(b), view(out, 0, ca, cb), L.PAD_ZERO, stream())
+        ctx.meta = (ca, cb)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        ca, cb = ctx.meta
+        g = _c(g)
+        n, h, w, _ = g.shape
+        da = db = None
+        if ctx.needs_input_grad[0]:
+            da = torch.empty((n, h, w, ca), dtype=g.dtype, device=g.device)
+            call("nemar_copy_view_bwd", view(da), view(g, 0, 0, ca), L.PAD_ZERO, 0, stream())
+        if ctx.needs_input_grad[1]:
+            db = torch.empty((n, h, w, cb), dtype=g.dtype, device=g.device)
+            call("nemar_copy_view_bwd", view(db), view(g, 0, ca, cb), L.PAD_ZERO, 0, stream())
+        return da, db
+
+
+# ------------------------------------------------------------------------------------------------
+# convolution
+# ------------------------------------------------------------------------------------------------
+class ConvCfg:
+    """Static description of one conv layer call (geometry + epilogue + engine choice)."""
+
+    def __init__(self, cin, cout, k, stride=1, pad=0, transposed=False, x_pad=0, act=L.ACT_NONE, stats=False,
+                 out_f32=False, out_pad_t=0, use_tc=False):
+        self.geom = L.ConvGeom(cin, cout, k, k, stride, pad, int(transposed))
+        self.cin, self.cout, self.k, self.stride, self.pad = cin, cout, k, stride, pad
+        self.transposed, self.x_pad, self.act, self.stats = transposed, x_pad, act, stats
+        self.out_f32, self.out_pad_t, self.use_tc = out_f32, out_pad_t, use_tc
+
+    def out_hw(self, h, w):
+        if not self.transposed:
+            f = lambda v: (v + 2 * self.pad - self.k) // self.stride + 1
+        else:
+            f = lambda v: (v - 1) * self.stride - 2 * self.pad + self.k + self.out_pad_t
+        return f(h), f(w)
+
+
+class PackedWeights:
+    """Per-parameter cache of the forward / backward packs (rebuilt when the weights epoch changes)."""
+
+    def __init__(self):
+        self.key = None
+        self.wf = self.wd = None
+
+    def get(self, weight, cfg, dtype):
+        key = (weights_epoch(), weight.data_ptr(), dtype)
+        if self.key != key:
+            g = cfg.geom
+            k2 = cfg.k * cfg.k
+            self.wf = torch.empty(cfg.cout * k2 * cfg.cin, dtype=dtype, device=weight.device)
+            self.wd = torch.empty(cfg.cin * k2 * cfg.cout, dtype=dtype, device=weight.device)
+            call("nemar_pack_weights", fptr(weight.detach()), g, L.dtype_code(self.wf), cfg.cin, cfg.cout,
+                 vptr(self.wf), vptr(self.wd), stream())
+            self.key = key
+        return self.wf, self.wd
+
+
+class Conv2dFn(Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, cfg, packed):
+        x = _c(x)
+        n, hp, wp, cin = x.shape
+        h, w = hp - 2 * cfg.x_pad, wp - 2 * cfg.x_pad
+        ho, wo = cfg.out_hw(h, w)
+        wf, wd = packed.get(weight, cfg, x.dtype)
+        ydt = torch.float32 if cfg.out_f32 else x.dtype
+        y = torch.empty((n, ho, wo, cfg.cout), dtype=ydt, device=x.device)
+        stats = None
+        if cfg.stats:
+            stats = torch.zeros((n, cfg.cout, 2), dtype=torch.float32, device=x.device)
+        call("nemar_conv2d_fprop", view(x, cfg.x_pad), vptr(wf), cfg.cin, fptr(bias.detach()) if bias is not None else None,
+             cfg.geom, cfg.act, view(y), fptr(stats), int(cfg.use_tc), stream())
+        ctx.cfg, ctx.wd = cfg, wd
+        ctx.has_bias = bias is not None
+        ctx.save_for_backward(x, weight, y if cfg.act != L.ACT_NONE else None)
+        if stats is None:
+            return y
+        ctx.mark_non_differentiable(stats)
+        return y, stats
+
+    @staticmethod
+    def backward(ctx, dy, dstats=None):
+        cfg = ctx.cfg
+        x, weight, y = ctx.saved_tensors
+        dy = _c(dy)
+        if cfg.act != L.ACT_NONE:
+            g = torch.empty_like(dy)
+            call("nemar_act_bwd", view(y), view(dy), cfg.act, view(g), stream())
+        else:
+            g = dy
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty_like(x)
+            call("nemar_conv2d_dgrad", view(g), vptr(ctx.wd), cfg.cout, cfg.geom, view(dx, cfg.x_pad),
+                 int(cfg.use_tc), stream())
+        if ctx.needs_input_grad[1]:
+            dw = torch.empty_like(weight)
+            xv, gv = view(x, cfg.x_pad), view(g)
+            ws_bytes = L.lib().nemar_conv2d_wgrad_workspace(L.C.byref(xv), L.C.byref(gv), L.C.byref(cfg.geom),
+                                                            int(cfg.use_tc))
+            ws = torch.empty(max(int(ws_bytes), 16), dtype=torch.uint8, device=x.device) if ws_bytes > 0 else None
+            call("nemar_conv2d_wgrad", xv, gv, cfg.geom, fptr(dw), vptr(ws), i64(ws_bytes), int(cfg.use_tc), stream())
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            db = torch.empty(cfg.cout, dtype=torch.float32, device=x.device)
+            call("nemar_bias_grad", view(g), fptr(db), stream())
+        return dx, dw, db, None, None
+
+
+# ------------------------------------------------------------------------------------------------
+# InstanceNorm + activation (+ residual) with halo
+# ------------------------------------------------------------------------------------------------
+class NormActFn(Function):
+    @staticmethod
+    def forward(ctx, x, stats, residual, act, res_pad, out_pad, pad_mode):
+        x = _c(x)
+        n, h, w, c = x.shape
+        y = torch.empty((n, h + 2 * out_pad, w + 2 * out_pad, c), dtype=x.dtype, device=x.device)
+        rv = None
+        if residual is not None:
+            residual = _c(residual)
+            rv = view(residual, res_pad)
+        call("nemar_norm_act_fwd", view(x), fptr(stats), act, rv, view(y, out_pad), pad_mode, stream())
+        ctx.meta = (act, res_pad, out_pad, pad_mode, residual.shape if residual is not None else None)
+        ctx.save_for_backward(x, stats)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        act, res_pad, out_pad, pad_mode, res_shape = ctx.meta
+        x, stats = ctx.saved_tensors
+        dy = _c(dy)
+        n, h, w, c = x.shape
+        red = None
+        if stats is not None:
+            red = torch.zeros((n, c, 2), dtype=torch.float32, device=x.device)
+            call("nemar_norm_act_bwd_reduce", view(x), fptr(stats), act, view(dy, out_pad), pad_mode, fptr(red),
+                 stream())
+        dx = torch.empty_like(x)
+        dres, drv = None, None
+        if res_shape is not None and ctx.needs_input_grad[2]:
+            dres = (torch.zeros if res_pad > 0 else torch.empty)(res_shape, dtype=x.dtype, device=x.device)
+            drv = view(dres, res_pad)
+        call("nemar_norm_act_bwd_apply", view(x), fptr(stats), act, view(dy, out_pad), pad_mode, fptr(red), view(dx),
+             drv, 0, stream())
+        return dx, None, dres, None, None, None, None
+
+
+class MaxPool2Fn(Function):
+    @staticmethod
+    def forward(ctx, x):
+        x = _c(x)
+        n, h, w, c = x.shape
+        y = torch.empty((n, h // 2, w // 2, c), dtype=x.dtype, device=x.device)
+        call("nemar_maxpool2_fwd", view(x), view(y), stream())
+        ctx.save_for_backward(x, y)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, y = ctx.saved_tensors
+        dy = _c(dy)
+        dx = torch.empty_like(x)
+        call("nemar_maxpool2_bwd", view(x), view(y), view(dy), view(dx), stream())
+        return dx
+
+
+class ResizeFn(Function):
+    """bilinear, align_corners=False, on engine tensors."""
+
+    @staticmethod
+    def forward(ctx, x, oh, ow):
+        x = _c(x)
+        n, h, w, c = x.shape
+        y = torch.empty((n, oh, ow, c), dtype=x.dtype, device=x.device)
+        call("nemar_bilinear_resize_fwd", view(x), view(y), stream())
+        ctx.meta = x.shape
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        dy = _c(dy)
+        dx = torch.empty(ctx.meta, dtype=dy.dtype, device=dy.device)
+        call("nemar_bilinear_resize_bwd", view(dy), view(dx), 0, stream())
+        return dx, None, None
+
+
+class ResizeNCHWFn(Function):
+    """bilinear, align_corners=False, on NCHW fp32 images (multi-resolution discriminator inputs)."""
+
+    @staticmethod
+    def forward(ctx, x, oh, ow):
+        x = _c(x)
+        n, c, h, w = x.shape
+        y = torch.empty((n, c, oh, ow), dtype=torch.float32, device=x.device)
+        call("nemar_bilinear_resize_nchw_fwd", fptr(x), n, c, h, w, fptr(y), oh, ow, stream())
+        ctx.meta = (n, c, h, w, oh, ow)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        n, c, h, w, oh, ow = ctx.meta
+        dy = _c(dy)
+        dx = torch.empty((n, c, h, w), dtype=torch.float32, device=dy.device)
+        call("nemar_bilinear_resize_nchw_bwd", fptr(dy), n, c, h, w, fptr(dx), oh, ow, stream())
+        return dx, None, None
+
+
+class DropoutFn(Function):
+    @staticmethod
+    def forward(ctx, x, seed, offset):
+        x = _c(x)
+        y = torch.empty_like(x)
+        call("nemar_dropout", view(x), view(y), L.u64(seed), L.u64(offset), stream())
+        ctx.meta = (seed, offset)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        dy = _c(dy)
+        dx = torch.empty_like(dy)
+        call("nemar_dropout", view(dy), view(dx), L.u64(ctx.meta[0]), L.u64(ctx.meta[1]), stream())
+        return dx, None, None
+
+
+# ------------------------------------------------------------------------------------------------
+# STN head
+# ------------------------------------------------------------------------------------------------
+class AffineGridFn(Function):
+    @staticmethod
+    def forward(ctx, theta, bx, by):
+        theta = _c(theta)
+        n = theta.shape[0]
+        h, w = by.numel(), bx.numel()
+        grid = torch.empty((n, h, w, 2), dtype=torch.float32, device=theta.device)
+        call("nemar_affine_grid_fwd", fptr(theta), fptr(bx), fptr(by), n, h, w, fptr(grid), stream())
+        ctx.save_for_backward(bx, by)
+        ctx.meta = (n, h, w)
+        return grid
+
+    @staticmethod
+    def backward(ctx, dgrid):
+        bx, by = ctx.saved_tensors
+        n, h, w = ctx.meta
+        dgrid = _c(dgrid)
+        dtheta = torch.empty((n, 6), dtype=torch.float32, device=dgrid.device)
+        call("nemar_affine_grid_bwd", fptr(dgrid), fptr(bx), fptr(by), n, h, w, fptr(dtheta), stream())
+        return dtheta, None, None
+
+
+class FlowGridFn(Function):
+    """grid[N,H,W,2] = identity(xs, ys) + offsets; offsets are the engine's channels-last fp32 conv output."""
+
+    @staticmethod
+    def forward(ctx, off, xs, ys):
+        off = _c(off)
+        n, h, w, two = off.shape
+        assert two == 2 and off.dtype == torch.float32
+        grid = torch.empty((n, h, w, 2), dtype=torch.float32, device=off.device)
+        call("nemar_flow_grid_fwd", fptr(off), i64(h * w * 2), i64(1), i64(w * 2), i64(2), fptr(xs), fptr(ys), n, h, w,
+             fptr(grid), stream())
+        return grid
+
+    @staticmethod
+    def backward(ctx, dgrid):
+        return dgrid, None, None
+
+
+class GridSampleFn(Function):
+    """bilinear / zeros / align_corners=False on one or two NCHW fp32 images sharing one grid."""
+
+    @staticmethod
+    def forward(ctx, grid, img0, img1):
+        grid, img0 = _c(grid), _c(img0)
+        n, c, h, w = img0.shape
+        ho, wo = grid.shape[1], grid.shape[2]
+        nimg = 1 if img1 is None else 2
+        out0 = torch.empty((n, c, ho, wo), dtype=torch.float32, device=grid.device)
+        out1 = None
+        if nimg == 2:
+            img1 = _c(img1)
+            out1 = torch.empty_like(out0)
+        call("nemar_grid_sample_fwd", fptr(img0), fptr(img1), nimg, n, c, h, w, fptr(grid), ho, wo, fptr(out0),
+             fptr(out1), None, stream())
+        ctx.save_for_backward(grid, img0, img1)
+        ctx.meta = (n, c, h, w, ho, wo, nimg)
+        if nimg == 1:
+            return out0
+        return out0, out1
+
+    @staticmethod
+    def backward(ctx, d0, d1=None):
+        grid, img0, img1 = ctx.saved_tensors
+        n, c, h, w, ho, wo, nimg = ctx.meta
+        dev = grid.device
+        d0 = _c(d0) if d0 is not None else torch.zeros((n, c, ho, wo), dtype=torch.float32, device=dev)
+        if nimg == 2:
+            d1 = _c(d1) if d1 is not None else torch.zeros((n, c, ho, wo), dtype=torch.float32, device=dev)
+        dimg0 = torch.zeros_like(img0) if ctx.needs_input_grad[1] else None
+        dimg1 = torch.zeros_like(img1) if (nimg == 2 and ctx.needs_input_grad[2]) else None
+        dgrid = torch.empty_like(grid)
+        call("nemar_grid_sample_bwd", fptr(img0), fptr(img1), nimg, n, c, h, w, fptr(grid), ho, wo, fptr(d0),
+             fptr(d1) if nimg == 2 else None, fptr(dimg0), fptr(dimg1), fptr(dgrid), stream())
+        return (dgrid if ctx.needs_input_grad[0] else None), dimg0, dimg1
+
+
+def grid_sample_indices(grid, img):
+    """Integer tap indices (x0,y0) the kernel uses for `grid` — the bit-exactness probe."""
+    grid, img = _c(grid), _c(img)
+    n, c, h, w = img.shape
+    ho, wo = grid.shape[1], grid.shape[2]
+    out = torch.empty((n, c, ho, wo), dtype=torch.float32, device=grid.device)
+    idx = torch.empty((n, ho, wo, 2), dtype=torch.int32, device=grid.device)
+    call("nemar_grid_sample_fwd", fptr(img), None, 1, n, c, h, w, fptr(grid), ho, wo, fptr(out), None,
+         vptr(idx), stream())
+    return out, idx
+
+
+class SmoothnessFn(Function):
+    """scale * smoothness_loss(offsets, img, alpha); offsets channels-last [N,H,W,2] fp32, img NCHW fp32."""
+
+    @staticmethod
+    def forward(ctx, off, img, alpha, scale):
+        off = _c(off)
+        n, h, w, _ = off.shape
+        loss = torch.zeros(1, dtype=torch.float32, device=off.device)
+        use_img = img is not None and alpha > 0.0
+        if use_img:
+            img = _c(img)
+            assert img.shape[0] == n and img.shape[2] == h and img.shape[3] == w
+        call("nemar_smoothness_fwd", fptr(off), i64(h * w * 2), i64(1), i64(w * 2), i64(2),
+             fptr(img) if use_img else None, int(img.shape[1]) if use_img else 0, float(alpha), n, h, w, float(scale),
+             fptr(loss), stream())
+        ctx.save_for_backward(off, img if use_img else None)
+        ctx.meta = (alpha, scale)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        off, img = ctx.saved_tensors
+        alpha, scale = ctx.meta
+        n, h, w, _ = off.shape
+        g = _c(g.reshape(1).to(torch.float32))
+        doff = torch.zeros_like(off)
+        call("nemar_smoothness_bwd", fptr(off), i64(h * w * 2), i64(1), i64(w * 2), i64(2), fptr(img),
+             int(img.shape[1]) if img is not None else 0, float(alpha), n, h, w, float(scale), fptr(g), fptr(doff),
+             stream())
+        return doff, None, None, None
+
+
+# ------------------------------------------------------------------------------------------------
+# losses, linear
+# ------------------------------------------------------------------------------------------------
+class L1Fn(Function):
+    @staticmethod
+    def forward(ctx, a, b, scale):
+        a, b = _c(a), _c(b)
+        out = torch.zeros(1, dtype=torch.float32, device=a.device)
+        call("nemar_l1_fwd", fptr(a), fptr(b), i64(a.numel()), float(scale), fptr(out), stream())
+        ctx.save_for_backward(a, b)
+        ctx.scale = scale
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        a, b = ctx.saved_tensors
+        g = _c(g.reshape(1).to(torch.float32))
+        da = torch.empty_like(a)
+        call("nemar_l1_bwd", fptr(a), fptr(b), i64(a.numel()), float(ctx.scale), fptr(g), fptr(da), 0, stream())
+        return da, None, None
+
+
+class MeanAbsFn(Function):
+    @staticmethod
+    def forward(ctx, a, scale):
+        a = _c(a)
+        out = torch.zeros(1, dtype=torch.float32, device=a.device)
+        call("nemar_mean_abs_fwd", fptr(a), i64(a.numel()), float(scale), fptr(out), stream())
+        ctx.save_for_backward(a)
+        ctx.scale = scale
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        (a,) = ctx.saved_tensors
+        g = _c(g.reshape(1).to(torch.float32))
+        da = torch.empty_like(a)
+        call("nemar_mean_abs_bwd", fptr(a), i64(a.numel()), float(ctx.scale), fptr(g), fptr(da), stream())
+        return da, None
+
+
+class MSEConstFn(Function):
+    """scale * mean((pred - target)^2) over an engine tensor (LSGAN, networks.py:237-238,273-275)."""
+
+    @staticmethod
+    def forward(ctx, pred, target, scale):
+        pred = _c(pred)
+        out = torch.zeros(1, dtype=torch.float32, device=pred.device)
+        call("nemar_mse_const_fwd", view(pred), float(target), float(scale), fptr(out), stream())
+        ctx.save_for_backward(pred)
+        ctx.meta = (target, scale)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        (pred,) = ctx.saved_tensors
+        target, scale = ctx.meta
+        g = _c(g.reshape(1).to(torch.float32))
+        dp = torch.empty_like(pred)
+        call("nemar_mse_const_bwd", view(pred), float(target), float(scale), fptr(g), view(dp), stream())
+        return dp, None, None
+
+
+class LinearFn(Function):
+    @staticmethod
+    def forward(ctx, x, w, b, act):
+        x = _c(x)
+        n, i = x.shape
+        o = w.shape[0]
+        y = torch.empty((n, o), dtype=torch.float32, device=x.device)
+        call("nemar_linear_fwd", fptr(x), fptr(w.detach()), fptr(b.detach()) if b is not None else None, n, i, o, act,
+             fptr(y), stream())
+        ctx.save_for_backward(x, w, y)
+        ctx.meta = (act, b is not None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w, y = ctx.saved_tensors
+        act, has_b = ctx.meta
+        dy = _c(dy)
+        n, i = x.shape
+        o = w.shape[0]
+        dx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
+        dw = torch.empty_like(w)
+        db = torch.empty(o, dtype=torch.float32, device=x.device) if has_b else None
+        call("nemar_linear_bwd", fptr(x), fptr(w.detach()), fptr(y), fptr(dy), n, i, o, act, fptr(dx), fptr(dw),
+             fptr(db), stream())
+        return dx, dw, db, None
+
+
+def adam_step(p, g, m, v, lr, beta1, beta2, eps, step, grad_scale=1.0):
+    call("nemar_adam_step", fptr(p), fptr(g), fptr(m), fptr(v), i64(p.numel()), float(lr), float(beta1), float(beta2),
+         float(eps), int(step), float(grad_scale), stream())

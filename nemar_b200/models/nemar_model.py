@@ -1,0 +1,160 @@
+"""NEMARModel on the B200 engine — the training hot path (reference models/nemar_model.py:12-288).
+
+Same plugin surface: flags, loss/visual/model names, set_input / forward / optimize_parameters, netT / netR /
+netD attributes and checkpoint keys.  Differences that are part of the design:
+  * one process per GPU; gradients of each optimizer phase are exchanged with ONE all-reduce on a flat bucket
+    (D bucket after backward_D, T+R bucket after backward_T_and_R — the reference's update order needs two);
+  * the three torch.optim.Adam instances become two flat-buffer Adam launches (D, and T+R);
+  * real_A resizes for the multi-resolution discriminators are computed once per step, not five times.
+"""
+import itertools
+
+import torch
+
+from . import networks
+from . import stn
+from .base_model import BaseModel
+from ..engine import functional as F
+from ..engine import parallel
+from ..engine.config import configure
+from ..engine.optim import FlatAdam
+
+
+class NEMARModel(BaseModel):
+    @staticmethod
+    def modify_commandline_options(parser, is_train=True):
+        parser = stn.modify_commandline_options(parser, is_train)
+        parser.add_argument("--precision", type=str, default="bf16", choices=["bf16", "fp32"],
+                            help="[engine] activation/weight storage dtype (accumulation is always fp32)")
+        parser.add_argument("--conv_engine", type=str, default="auto", choices=["auto", "generic"],
+                            help="[engine] auto: tcgen05 where supported; generic: CUDA-core kernels only")
+        if is_train:
+            parser.add_argument("--lambda_GAN", type=float, default=1.0, help="weight of the GAN loss")
+            parser.add_argument("--lambda_recon", type=float, default=100.0, help="weight of the L1 reconstruction loss")
+            parser.add_argument("--lambda_smooth", type=float, default=0.0, help="weight of the STN regulariser")
+            parser.add_argument("--enable_tbvis", action="store_true", help="tensorboard visualizer (not part of the engine)")
+            parser.add_argument("--multi_resolution", type=int, default=1, help="number of discriminator scales")
+        return parser
+
+    def __init__(self, opt):
+        BaseModel.__init__(self, opt)
+        configure(getattr(opt, "precision", "bf16"), getattr(opt, "conv_engine", "auto"))
+        self.train_stn = True
+        self.setup_visualizers()
+        self.tb_visualizer = None        # train.py reads this attribute (reference train.py:77-81)
+        self.define_networks()
+        if self.isTrain:
+            self.criterionGAN = networks.GANLoss(opt.gan_mode).to(self.device)
+            self.setup_optimizers()
+
+    def setup_visualizers(self):
+        self.loss_names = ["L1_TR", "GAN_TR", "L1_RT", "GAN_RT", "smoothness", "D_fake_TR", "D_fake_RT", "D"]
+        self.visual_names = ["real_A", "real_B", "fake_TR_B", "fake_RT_B", "registered_real_A", "fake_B"]
+        self.model_names = ["T", "R"] + (["D"] if self.isTrain else [])
+
+    def define_networks(self):
+        opt = self.opt
+        AtoB = opt.direction == "AtoB"
+        in_c = opt.input_nc if AtoB else opt.output_nc
+        out_c = opt.output_nc if AtoB else opt.input_nc
+        self.netT = networks.define_G(in_c, out_c, opt.ngf, opt.netG, opt.norm, not opt.no_dropout, opt.init_type,
+                                      opt.init_gain, self.gpu_ids)
+        self.netR = stn.define_stn(opt, opt.stn_type)
+        if self.isTrain:
+            mk = lambda: networks.define_D(opt.output_nc + opt.input_nc, opt.ndf, opt.netD, opt.n_layers_D, opt.norm,
+                                           opt.init_type, opt.init_gain, self.gpu_ids)
+            self.netD = mk()
+            self.netD_multiresolution = [mk() for _ in range(max(opt.multi_resolution - 1, 0))]
+
+    def reset_weights(self):
+        opt = self.opt
+        for net in [self.netT, self.netD, *self.netD_multiresolution]:
+            networks.init_weights(net, opt.init_type, opt.init_gain)
+
+    def setup_optimizers(self):
+        opt = self.opt
+        betas = (opt.beta1, 0.999)
+        # R and T are always stepped together (reference :282-283) -> one flat bucket, one launch
+        self.optimizer_TR = FlatAdam(itertools.chain(self.netR.parameters(), self.netT.parameters()), lr=opt.lr, betas=betas)
+        d_params = itertools.chain(self.netD.parameters(), *[x.parameters() for x in self.netD_multiresolution])
+        self.optimizer_D = FlatAdam(d_params, lr=opt.lr, betas=betas)
+        self.optimizer_R = self.optimizer_T = self.optimizer_TR      # reference attribute names
+        self.optimizers += [self.optimizer_TR, self.optimizer_D]
+        hook = parallel.BucketAllReduce()
+        self.optimizer_TR.grad_hook = hook
+        self.optimizer_D.grad_hook = hook
+        self.allreduce = hook
+
+    def set_input(self, input):
+        AtoB = self.opt.direction == "AtoB"
+        a, b = ("A", "B") if AtoB else ("B", "A")
+        self.real_A = input[a].to(self.device, non_blocking=True).float().contiguous()
+        self.real_B = input[b].to(self.device, non_blocking=True).float().contiguous()
+        self.image_paths = input.get(a + "_paths", [])
+
+    def forward(self):
+        self.fake_B = self.netT(self.real_A)
+        warped, reg_term = self.netR(self.real_A, self.real_B, apply_on=[self.real_A, self.fake_B])
+        self.stn_reg_term = reg_term
+        self.registered_real_A = warped[0]
+        self.fake_TR_B = self.netT(self.registered_real_A)   # registration first, then translation
+        self.fake_RT_B = warped[1]                           # translation first, then registration
+
+    # -- discriminator plumbing --------------------------------------------------------------------
+    def _scales(self):
+        return [self.netD] + list(self.netD_multiresolution)
+
+    def _resized(self, img, level):
+        if level == 0:
+            return img
+        sh, sw = self.real_A.size(2) // (2 ** level), self.real_A.size(3) // (2 ** level)
+        return F.ResizeNCHWFn.apply(img, sh, sw)
+
+    def _real_A_pyramid(self):
+        return [self._resized(self.real_A, i) for i in range(len(self._scales()))]
+
+    def _gan(self, pyr_A, img_B, target_is_real, detach):
+        """sum over scales of GANLoss(D_i(cat(A_i, B_i)))"""
+        total = None
+        for i, netD in enumerate(self._scales()):
+            b = img_B.detach() if detach else img_B
+            pred = netD.forward_engine(pyr_A[i], self._resized(b, i))
+            term = self.criterionGAN(pred, target_is_real)
+            total = term if total is None else total + term
+        return total
+
+    def backward_T_and_R(self):
+        opt = self.opt
+        pyr_A = self._real_A_pyramid()
+        self.loss_L1_TR = F.L1Fn.apply(self.fake_TR_B, self.real_B, opt.lambda_recon).squeeze(0)
+        self.loss_GAN_TR = opt.lambda_GAN * self._gan(pyr_A, self.fake_TR_B, True, detach=False)
+        self.loss_L1_RT = F.L1Fn.apply(self.fake_RT_B, self.real_B, opt.lambda_recon).squeeze(0)
+        self.loss_GAN_RT = opt.lambda_GAN * self._gan(pyr_A, self.fake_RT_B, True, detach=False)
+        self.loss_smoothness = opt.lambda_smooth * self.stn_reg_term
+        loss = self.loss_L1_TR + self.loss_L1_RT + self.loss_GAN_TR + self.loss_GAN_RT + self.loss_smoothness
+        loss.backward()
+        return loss
+
+    def backward_D(self):
+        pyr_A = self._real_A_pyramid()
+        loss_D_real = self._gan(pyr_A, self.real_B, True, detach=True)
+        self.loss_D_fake_TR = self._gan(pyr_A, self.fake_TR_B, False, detach=True)
+        self.loss_D_fake_RT = self._gan(pyr_A, self.fake_RT_B, False, detach=True)
+        self.loss_D = 0.5 * self.opt.lambda_GAN * (loss_D_real + self.loss_D_fake_TR + self.loss_D_fake_RT)
+        self.loss_D.backward()
+        return self.loss_D
+
+    def optimize_parameters(self):
+        self.forward()
+        # D phase
+        self.set_requires_grad([self.netT, self.netR], False)
+        self.optimizer_D.zero_grad()
+        self.backward_D()
+        self.optimizer_D.step()           # all-reduce of the D bucket + flat Adam
+        self.set_requires_grad([self.netT, self.netR], True)
+        # T + R phase (uses the UPDATED discriminator, as the reference does)
+        self.set_requires_grad([self.netD, *self.netD_multiresolution], False)
+        self.optimizer_TR.zero_grad()
+        self.backward_T_and_R()
+        self.optimizer_TR.step()          # all-reduce of the T+R bucket + flat Adam
+        self.set_requires_grad([self.netD, *self.netD_multiresolution], True)

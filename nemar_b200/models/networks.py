@@ -1,0 +1,287 @@
+"""Translation network (ResNet generator), PatchGAN discriminator, GAN objective and weight init, rebuilt
+on the B200 engine.  Mirrors the reference's factory surface and parameter tree
+(models/networks.py:62-209,215-281,323-446,556-602): same `define_G/define_D/GANLoss/init_weights` names and
+arguments, same state_dict keys (`model.1.weight`, `model.10.conv_block.5.bias`, ...), so checkpoints
+interchange with the reference.  Everything below nn.Module.forward is libnemar_b200.so.
+"""
+import torch
+import torch.nn as nn
+
+from ..engine import functional as F
+from ..engine import lib as L
+from ..engine.config import CONFIG
+
+
+# ------------------------------------------------------------------------------------------------
+# parameter holders
+# ------------------------------------------------------------------------------------------------
+class Holder(nn.Module):
+    """Anonymous container used to reproduce the reference's attribute paths."""
+
+    def forward(self, *a, **k):  # pragma: no cover - containers are never called
+        raise RuntimeError("container module")
+
+
+def tc_policy(cin, cout, k, stride, transposed, dtype):
+    """Should this layer run on the tcgen05 engine?"""
+    if CONFIG.conv_engine != "auto" or dtype != torch.bfloat16:
+        return False
+    geom = L.ConvGeom(cin, cout, k, k, stride, 0, int(transposed))
+    return bool(L.lib().nemar_conv2d_tc_supported(L.C.byref(geom), L.BF16, 0, 0))
+
+
+class Conv(nn.Module):
+    """Owns `weight`/`bias` in the reference layout and runs the conv through the engine."""
+
+    def __init__(self, cin, cout, k, stride=1, pad=0, bias=True, transposed=False, out_pad_t=0):
+        super().__init__()
+        shape = (cin, cout, k, k) if transposed else (cout, cin, k, k)
+        self.weight = nn.Parameter(torch.empty(shape))
+        self.bias = nn.Parameter(torch.zeros(cout)) if bias else None
+        nn.init.normal_(self.weight, 0.0, 0.02)
+        self.meta = (cin, cout, k, stride, pad, transposed, out_pad_t)
+        self._packed = F.PackedWeights()
+        self._cfgs = {}
+
+    def extra_repr(self):
+        cin, cout, k, s, p, t, _ = self.meta
+        return "%d->%d k%d s%d p%d%s" % (cin, cout, k, s, p, " transposed" if t else "")
+
+    def run(self, x, x_pad=0, act=L.ACT_NONE, stats=False, out_f32=False):
+        cin, cout, k, stride, pad, transposed, opt = self.meta
+        key = (x_pad, act, stats, out_f32, x.dtype, CONFIG.conv_engine)
+        cfg = self._cfgs.get(key)
+        if cfg is None:
+            use_tc = (not out_f32) and tc_policy(cin, cout, k, stride, transposed, x.dtype)
+            cfg = F.ConvCfg(cin, cout, k, stride, pad, transposed, x_pad, act, stats, out_f32, opt, use_tc)
+            self._cfgs[key] = cfg
+        return F.Conv2dFn.apply(x, self.weight, self.bias, cfg, self._packed)
+
+
+def norm_act(x, stats, act, residual=None, res_pad=0, out_pad=0, pad_mode=L.PAD_REFLECT):
+    return F.NormActFn.apply(x, stats, residual, act, res_pad, out_pad, pad_mode)
+
+
+def conv_in_act(conv, x, x_pad, act, out_pad=0, residual=None, res_pad=0):
+    """conv -> InstanceNorm (statistics from the conv epilogue) -> act (+residual) -> optional reflect halo"""
+    y, st = conv.run(x, x_pad=x_pad, stats=True)
+    return norm_act(y, st, act, residual, res_pad, out_pad)
+
+
+def conv_act(conv, x, x_pad, act, out_pad=0, out_f32=False):
+    """conv -> act with no normalisation; a reflect halo on the result needs the separate pass"""
+    if out_pad == 0:
+        return conv.run(x, x_pad=x_pad, act=act, out_f32=out_f32)
+    y = conv.run(x, x_pad=x_pad)
+    return norm_act(y, None, act, None, 0, out_pad)
+
+
+class ResnetBlock(nn.Module):
+    """x + IN(conv(pad(relu(IN(conv(pad(x))))))) (reference networks.py:389-446), reflect padding."""
+
+    def __init__(self, dim, use_dropout=False, use_bias=True):
+        super().__init__()
+        self.conv_block = Holder()
+        self.conv_block.add_module("1", Conv(dim, dim, 3, 1, 1, bias=use_bias))
+        self.second = "6" if use_dropout else "5"
+        self.conv_block.add_module(self.second, Conv(dim, dim, 3, 1, 1, bias=use_bias))
+        self.use_dropout = use_dropout
+        self._drop_calls = 0
+
+    def run(self, t_padded, out_pad):
+        """t_padded carries a reflect halo of 1 (it is both the conv input and the skip)."""
+        c1 = getattr(self.conv_block, "1")
+        c2 = getattr(self.conv_block, self.second)
+        if self.use_dropout and self.training:
+            u = conv_in_act(c1, t_padded, 1, L.ACT_RELU, out_pad=0)
+            self._drop_calls += 1
+            u = F.DropoutFn.apply(u, CONFIG.dropout_seed + id(self) % 65521, self._drop_calls * u.numel())
+            u = norm_act(u, None, L.ACT_NONE, None, 0, 1)
+        else:
+            u = conv_in_act(c1, t_padded, 1, L.ACT_RELU, out_pad=1)
+        return conv_in_act(c2, u, 1, L.ACT_NONE, out_pad=out_pad, residual=t_padded, res_pad=1)
+
+
+class ResnetGenerator(nn.Module):
+    """Reference networks.py:323-386.  NCHW fp32 in, NCHW fp32 out."""
+
+    def __init__(self, input_nc, output_nc, ngf=64, use_dropout=False, n_blocks=6, use_bias=True):
+        super().__init__()
+        assert n_blocks >= 0
+        self.n_blocks, self.input_nc, self.output_nc = n_blocks, input_nc, output_nc
+        m = Holder()
+        m.add_module("1", Conv(input_nc, ngf, 7, 1, 3, bias=use_bias))
+        m.add_module("4", Conv(ngf, ngf * 2, 3, 2, 1, bias=use_bias))
+        m.add_module("7", Conv(ngf * 2, ngf * 4, 3, 2, 1, bias=use_bias))
+        for i in range(n_blocks):
+            m.add_module(str(10 + i), ResnetBlock(ngf * 4, use_dropout, use_bias))
+        b = 10 + n_blocks
+        m.add_module(str(b), Conv(ngf * 4, ngf * 2, 3, 2, 1, bias=use_bias, transposed=True, out_pad_t=1))
+        m.add_module(str(b + 3), Conv(ngf * 2, ngf, 3, 2, 1, bias=use_bias, transposed=True, out_pad_t=1))
+        m.add_module(str(b + 7), Conv(ngf, output_nc, 7, 1, 3, bias=True))
+        self.model = m
+
+    def forward(self, x):
+        m, nb = self.model, self.n_blocks
+        g = lambda i: getattr(m, str(i))
+        t = F.ImagesToNHWC.apply(3, L.PAD_REFLECT, CONFIG.dtype, self.input_nc, x)
+        t = conv_in_act(g(1), t, 3, L.ACT_RELU)
+        t = conv_in_act(g(4), t, 0, L.ACT_RELU)
+        t = conv_in_act(g(7), t, 0, L.ACT_RELU, out_pad=1 if nb > 0 else 0)
+        for i in range(nb):
+            t = g(10 + i).run(t, out_pad=1 if i + 1 < nb else 0)
+        b = 10 + nb
+        t = conv_in_act(g(b), t, 0, L.ACT_RELU)
+        t = conv_in_act(g(b + 3), t, 0, L.ACT_RELU, out_pad=3)
+        y = g(b + 7).run(t, x_pad=3, act=L.ACT_TANH, out_f32=True)
+        return F.ToNCHW.apply(y, self.output_nc)
+
+
+class NLayerDiscriminator(nn.Module):
+    """70x70 PatchGAN (reference networks.py:556-602).  `forward` keeps the reference signature (NCHW in,
+    NCHW out); `forward_engine` takes the images to concatenate and returns the engine-layout prediction."""
+
+    def __init__(self, input_nc, ndf=64, n_layers=3, use_bias=True):
+        super().__init__()
+        self.input_nc, self.n_layers = input_nc, n_layers
+        m = Holder()
+        m.add_module("0", Conv(input_nc, ndf, 4, 2, 1, bias=True))
+        nf, idx, self.mid = 1, 2, []
+        for n in range(1, n_layers):
+            nf_prev, nf = nf, min(2 ** n, 8)
+            m.add_module(str(idx), Conv(ndf * nf_prev, ndf * nf, 4, 2, 1, bias=use_bias))
+            self.mid.append(idx)
+            idx += 3
+        nf_prev, nf = nf, min(2 ** n_layers, 8)
+        m.add_module(str(idx), Conv(ndf * nf_prev, ndf * nf, 4, 1, 1, bias=use_bias))
+        self.mid.append(idx)
+        idx += 3
+        m.add_module(str(idx), Conv(ndf * nf, 1, 4, 1, 1, bias=True))
+        self.last = idx
+        self.model = m
+
+    def forward_engine(self, *imgs):
+        m = self.model
+        t = F.ImagesToNHWC.apply(0, L.PAD_ZERO, CONFIG.dtype, self.input_nc, *imgs)
+        t = getattr(m, "0").run(t, act=L.ACT_LRELU)
+        for idx in self.mid:
+            t = conv_in_act(getattr(m, str(idx)), t, 0, L.ACT_LRELU)
+        return getattr(m, str(self.last)).run(t, out_f32=True)   # [N,h,w,1] fp32
+
+    def forward(self, x):
+        return F.ToNCHW.apply(self.forward_engine(x), 1)
+
+
+# ------------------------------------------------------------------------------------------------
+# GAN objective
+# ------------------------------------------------------------------------------------------------
+class GANLoss(nn.Module):
+    """Reference networks.py:215-281.  lsgan is the engine path (MSE against a constant, fused);
+    'vanilla'/'wgangp' are accepted for interface parity and evaluated with torch ops (not on the
+    benchmarked configurations, which all pass --gan_mode lsgan)."""
+
+    def __init__(self, gan_mode, target_real_label=1.0, target_fake_label=0.0):
+        super().__init__()
+        if gan_mode not in ("lsgan", "vanilla", "wgangp"):
+            raise NotImplementedError("gan mode %s not implemented" % gan_mode)
+        self.register_buffer("real_label", torch.tensor(target_real_label))
+        self.register_buffer("fake_label", torch.tensor(target_fake_label))
+        self.gan_mode = gan_mode
+        self.real_value, self.fake_value = float(target_real_label), float(target_fake_label)
+
+    def __call__(self, prediction, target_is_real):
+        target = self.real_value if target_is_real else self.fake_value
+        if self.gan_mode == "lsgan":
+            if prediction.dim() == 4 and prediction.shape[1] == 1 and prediction.shape[3] != 1:
+                prediction = prediction.permute(0, 2, 3, 1)   # NCHW [N,1,h,w] -> same memory as [N,h,w,1]
+            return F.MSEConstFn.apply(prediction.contiguous(), target, 1.0).squeeze(0)
+        if self.gan_mode == "vanilla":
+            return torch.nn.functional.binary_cross_entropy_with_logits(prediction, torch.full_like(prediction, target))
+        return -prediction.mean() if target_is_real else prediction.mean()
+
+
+# ------------------------------------------------------------------------------------------------
+# init + factories
+# ------------------------------------------------------------------------------------------------
+def init_weights(net, init_type="normal", init_gain=0.02):
+    """Reference networks.py:62-95: conv/linear weights by `init_type`, biases zero."""
+    def init_func(m):
+        if isinstance(m, (Conv, nn.Linear)) and getattr(m, "weight", None) is not None:
+            if init_type == "normal":
+                nn.init.normal_(m.weight.data, 0.0, init_gain)
+            elif init_type == "xavier":
+                nn.init.xavier_normal_(m.weight.data, gain=init_gain)
+            elif init_type == "kaiming":
+                nn.init.kaiming_normal_(m.weight.data, a=0, mode="fan_in")
+            elif init_type == "orthogonal":
+                nn.init.orthogonal_(m.weight.data, gain=init_gain)
+            else:
+                raise NotImplementedError("initialization method [%s] is not implemented" % init_type)
+            if m.bias is not None:
+                nn.init.constant_(m.bias.data, 0.0)
+
+    print("initialize network with %s" % init_type)
+    net.apply(init_func)
+    F.bump_weights_epoch()
+
+
+def init_net(net, init_type="normal", init_gain=0.02, gpu_ids=()):
+    """One replica per process: no DataParallel wrapper (reference networks.py:98-113)."""
+    init_weights(net, init_type, init_gain)
+    if len(gpu_ids) > 0:
+        assert torch.cuda.is_available()
+        net.to(torch.device("cuda", torch.cuda.current_device()))
+    return net
+
+
+def define_G(input_nc, output_nc, ngf, netG, norm="instance", use_dropout=False, init_type="normal", init_gain=0.02,
+             gpu_ids=()):
+    if norm != "instance":
+        raise NotImplementedError("the B200 engine implements --norm instance (the NeMAR default); got [%s]" % norm)
+    blocks = {"resnet_9blocks": 9, "resnet_6blocks": 6, "resnet_5blocks": 5, "resnet_4blocks": 4, "resnet_3blocks": 3}
+    if netG not in blocks:
+        raise NotImplementedError("Generator model name [%s] is not recognized" % netG)
+    net = ResnetGenerator(input_nc, output_nc, ngf, use_dropout=use_dropout, n_blocks=blocks[netG])
+    return init_net(net, init_type, init_gain, gpu_ids)
+
+
+def define_D(input_nc, ndf, netD, n_layers_D=3, norm="instance", init_type="normal", init_gain=0.02, gpu_ids=()):
+    if norm != "instance":
+        raise NotImplementedError("the B200 engine implements --norm instance (the NeMAR default); got [%s]" % norm)
+    if netD == "basic":
+        net = NLayerDiscriminator(input_nc, ndf, n_layers=3)
+    elif netD == "n_layers":
+        net = NLayerDiscriminator(input_nc, ndf, n_layers=n_layers_D)
+    else:
+        raise NotImplementedError("Discriminator model name [%s] is not recognized" % netD)
+    return init_net(net, init_type, init_gain, gpu_ids)
+
+
+def get_scheduler(optimizer, opt):
+    """Reference networks.py:32-59 builds torch schedulers that train.py never steps; the engine keeps the
+    attribute (a callable returning the lr multiplier) so BaseModel.update_learning_rate works."""
+    if opt.lr_policy == "linear":
+        def rule(epoch):
+            return 1.0 - max(0, epoch + opt.epoch_count - opt.niter) / float(opt.niter_decay + 1)
+    elif opt.lr_policy == "step":
+        def rule(epoch):
+            return 0.1 ** (epoch // opt.lr_decay_iters)
+    elif opt.lr_policy == "cosine":
+        import math
+
+        def rule(epoch):
+            return 0.5 * (1.0 + math.cos(math.pi * epoch / max(opt.niter, 1)))
+    else:
+        raise NotImplementedError("learning rate policy [%s] is not implemented" % opt.lr_policy)
+    return LambdaSchedule(optimizer, rule)
+
+
+class LambdaSchedule:
+    def __init__(self, optimizer, rule):
+        self.optimizer, self.rule, self.epoch = optimizer, rule, 0
+        self.base_lr = optimizer.param_groups[0]["lr"]
+
+    def step(self, *_):
+        self.epoch += 1
+        for g in self.optimizer.param_groups:
+            g["lr"] = self.base_lr * self.rule(self.epoch)
