@@ -1,0 +1,309 @@
+"""bench.py — paired 256x256 samples/sec of NeMAR's training step (NEMARModel.optimize_parameters) on B200.
+
+    python bench.py --gpus N --steps K --warmup W            # this engine (one rank per GPU under torchrun)
+    python bench.py --impl reference --gpus N --steps K ...   # the reference's CPU path (oracle port) on host cores
+
+Workload (BASELINE.json configs[1]): 256x256 synthetic A/B ~ U(-1,1), --stn_type unet (cfg A), resnet_9blocks
+generator, PatchGAN, LSGAN, --no_dropout, bf16 storage / fp32 accumulate, 16 paired samples per GPU (weak
+scaling).  One "step" = forward + D step + T/R step, including both gradient all-reduces and both Adam updates.
+Prints ONE JSON line (rank 0).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+HW = 256
+PER_GPU_BATCH = 16
+CONV_GFLOP_PER_SAMPLE = 724.72     # algorithmic conv FLOPs (2*MAC, fwd+bwd) per paired sample
+WORKLOAD = "C2: 256x256 synthetic A/B, unet STN cfg A + resnet_9blocks + PatchGAN, lsgan, no_dropout, batch 16/GPU"
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sustained=d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                    source="measured (MEASURED_PEAKS.json)")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, source="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = sorted(float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit())
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 7:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx[0] if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def build_engine_model(per_gpu_batch, size=HW, precision="bf16", conv_engine="auto", netG="resnet_9blocks",
+                       stn_type="unet"):
+    from nemar_b200.engine import functional as F
+    from nemar_b200.models import create_model
+    from nemar_b200.options.train_options import TrainOptions
+    argv = ["--dataroot", "none", "--name", "bench", "--checkpoints_dir", "/tmp/nemar_b200_bench", "--gpu_ids",
+            str(int(os.environ.get("LOCAL_RANK", "0"))), "--gan_mode", "lsgan", "--no_dropout", "--stn_type", stn_type,
+            "--netG", netG, "--img_height", str(size), "--img_width", str(size), "--batch_size", str(per_gpu_batch),
+            "--dataset_mode", "synthetic", "--precision", precision, "--conv_engine", conv_engine]
+    opt = TrainOptions().parse(argv, quiet=True)
+    torch.manual_seed(0)          # identical initial replicas on every rank
+    model = create_model(opt)
+    F.bump_weights_epoch()
+    return model, opt
+
+
+def run_engine(args):
+    from nemar_b200.engine import lib as L
+    from nemar_b200.engine import parallel
+    import torch.distributed as dist
+    world, rank, local = parallel.init_process_group_from_env()
+    assert world == args.gpus, "launch with torchrun --nproc-per-node %d (WORLD_SIZE=%d)" % (args.gpus, world)
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    peaks = load_peaks()
+    model, opt = build_engine_model(args.batch, args.size, args.precision, args.conv_engine)
+    # the global batch is drawn once (seed 1) and sliced by rank so that 1-GPU and N-GPU runs see the same data
+    g = torch.Generator().manual_seed(1)
+    A_all = torch.rand((args.batch * world, 3, args.size, args.size), generator=g) * 2 - 1
+    B_all = torch.rand((args.batch * world, 3, args.size, args.size), generator=g) * 2 - 1
+    A_host = parallel.shard_batch(A_all, rank, world).contiguous().pin_memory()
+    B_host = parallel.shard_batch(B_all, rank, world).contiguous().pin_memory()
+    A_dev, B_dev = A_host.to(dev), B_host.to(dev)
+    dev_batch = {"A": A_dev, "B": B_dev, "A_paths": "", "B_paths": ""}
+    host_batch = {"A": A_host, "B": B_host, "A_paths": "", "B_paths": ""}
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(batch, steps, read_loss):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            model.set_input(batch)
+            model.optimize_parameters()
+            if read_loss:
+                _ = float(model.loss_D)        # device -> host read of the step's result
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms)
+
+    for _ in range(max(args.warmup, 3)):
+        model.set_input(dev_batch)
+        model.optimize_parameters()
+    torch.cuda.synchronize()
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    L.COUNTERS["launches"] = 0
+    L.TIMER.enable(args.kernel_timing)
+    ms = timed(dev_batch, args.steps, read_loss=False)
+    launches = L.COUNTERS["launches"]
+    kstats = L.TIMER.collect()
+    L.TIMER.enable(False)
+    clocks = sampler.stop() if rank == 0 else None
+    ms_e2e = timed(host_batch, args.steps, read_loss=True)
+
+    global_batch = args.batch * world
+    value = global_batch * args.steps / (ms / 1e3)
+    e2e_value = global_batch * args.steps / (ms_e2e / 1e3)
+    if rank != 0:
+        return
+    # ---- roofline of the dominant kernel (largest share of timed kernel time)
+    roof = None
+    if kstats:
+        name, st = max(kstats.items(), key=lambda kv: kv[1]["ms"])
+        tf = st["flops"] / (st["ms"] / 1e3) / 1e12 if st["ms"] > 0 else 0.0
+        tot_ms = sum(v["ms"] for v in kstats.values())
+        roof = {"bound": "tensor", "kernel": name, "achieved": round(tf, 2), "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
+                "frac": round(tf / peaks["tf_sustained"], 4), "traffic": None, "peak_source": peaks["source"] + ", sustained",
+                "launches": st["n"], "avg_launch_ms": round(st["ms"] / max(st["n"], 1), 4),
+                "share_of_timed_kernels": round(st["ms"] / max(tot_ms, 1e-9), 4),
+                "by_kernel": {k: {"ms": round(v["ms"], 3), "n": v["n"],
+                                  "tflops": round(v["flops"] / max(v["ms"], 1e-9) / 1e9, 2),
+                                  "top": dict(sorted(((a, round(b, 3)) for a, b in v["top"].items()), key=lambda t: -t[1])[:4])}
+                              for k, v in sorted(kstats.items(), key=lambda kv: -kv[1]["ms"])}}
+    conv_frac = value * CONV_GFLOP_PER_SAMPLE * 1e9 / (world * peaks["tf_sustained"] * 1e12) if args.size == HW else None
+    out = {"metric": "paired 256x256 samples/sec", "value": round(value, 3), "unit": "samples/s", "n_gpus": world,
+           "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": round(ms / args.steps, 3),
+           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
+           "config": {"workload": WORKLOAD if (args.size == HW and args.batch == PER_GPU_BATCH) else
+                      "%dx%d unet STN + resnet_9blocks, batch %d/GPU" % (args.size, args.size, args.batch),
+                      "global_batch": global_batch, "parallelism": "dp%d" % world, "conv_engine": args.conv_engine,
+                      "l2": "inputs larger than L2: a step streams several GB of activations, no flush needed",
+                      "allreduce_per_step": 2},
+           "clocks": clocks,
+           "e2e": {"value": round(e2e_value, 3), "unit": "samples/s", "h2d_bytes_per_step": int(A_host.numel() * 4 * 2),
+                   "d2h_bytes_per_step": 4, "ms_per_step": round(ms_e2e / args.steps, 3)},
+           "gpu_launches": int(launches),
+           "conv_roofline_frac_whole_step": round(conv_frac, 4) if conv_frac is not None else None,
+           "roofline": roof}
+    if world == 1 and not args.no_cpu_baseline:
+        out["cpu_baseline"] = cpu_baseline(args.size, budget_s=15.0)
+    if args.grid_sample_bench:
+        out["grid_sample"] = grid_sample_bench(dev, peaks)
+    print(json.dumps(out))
+
+
+def cpu_baseline(size, budget_s, batch=2, stn_type="unet", n_blocks=9):
+    """The oracle port of the reference's CPU path, timed on this box's host cores on a bounded sample."""
+    from oracle import nemar_oracle as O
+    torch.set_num_threads(os.cpu_count() or 1)
+    cfg = O.OracleConfig(stn_type=stn_type, n_blocks=n_blocks, height=size, width=size)
+    T, R, Ds = O.make_states(cfg, seed=0, live_head=False)
+    A, B = O.synthetic_batch(batch, size, size, seed=1)
+    st = O.OracleStep(cfg, T, R, Ds)
+    st.step(A, B)                                   # warm-up
+    t0, n = time.time(), 0
+    while n < 1 or (time.time() - t0 < budget_s and n < 50):
+        st.step(A, B)
+        n += 1
+    dt = time.time() - t0
+    return {"value": round(batch * n / dt, 4), "unit": "samples/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": "%d optimize_parameters steps of the %dx%d unet/resnet_%d workload at batch %d, fp32, torch CPU "
+                      "(the reference's own ATen path restated in oracle/nemar_oracle.py)" % (n, size, size, n_blocks, batch)}
+
+
+def run_reference(args):
+    """`--impl reference`: the reference's own CPU implementation of the path (oracle port), all host threads.
+    Under torchrun only rank 0 works."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    from oracle import nemar_oracle as O
+    torch.set_num_threads(os.cpu_count() or 1)
+    batch = 2
+    cfg = O.OracleConfig(stn_type="unet", n_blocks=9, height=args.size, width=args.size)
+    T, R, Ds = O.make_states(cfg, seed=0, live_head=False)
+    A, B = O.synthetic_batch(batch, args.size, args.size, seed=1)
+    st = O.OracleStep(cfg, T, R, Ds)
+    for _ in range(max(1, min(args.warmup, 2))):
+        st.step(A, B)
+    steps = max(1, min(args.steps, 10))
+    t0 = time.time()
+    for _ in range(steps):
+        st.step(A, B)
+    dt = time.time() - t0
+    value = batch * steps / dt
+    sample = "each step = one optimize_parameters at batch %d (bounded sample of the batch-16 workload; CPU samples/s is " \
+             "batch-insensitive), fp32, %d threads" % (batch, torch.get_num_threads())
+    print(json.dumps({"impl": "reference", "metric": "paired 256x256 samples/sec", "value": round(value, 4), "unit": "samples/s",
+                      "n_gpus": args.gpus, "steps": steps, "warmup": max(1, min(args.warmup, 2)),
+                      "ms_per_step": round(dt / steps * 1e3, 2), "higher_is_better": True, "scaling": "weak",
+                      "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
+                      "config": {"workload": WORKLOAD, "global_batch": batch, "parallelism": "cpu"},
+                      "cpu_baseline": {"value": round(value, 4), "unit": "samples/s", "cores": torch.get_num_threads(),
+                                       "kind": "port", "sample": sample},
+                      "e2e": {"value": round(value, 4), "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+def grid_sample_bench(dev, peaks, size=1024, n=4, iters=20):
+    """grid_sample HBM GB/s (second half of BASELINE.json's metric): 1024x1024, C=3, fp32, near-identity grid;
+    algorithmic bytes per output pixel from SURVEY.md section 8d (fwd 32 B; bwd with grad_input 52 B)."""
+    from nemar_b200.engine import functional as F
+    g = torch.Generator().manual_seed(0)
+    img = (torch.rand((n, 3, size, size), generator=g) * 2 - 1).to(dev)
+    xs = torch.linspace(-1, 1, size)
+    ident = torch.stack([xs.view(1, size).expand(size, size), xs.view(size, 1).expand(size, size)], -1)
+    grid = (ident.unsqueeze(0) + torch.randn((n, size, size, 2), generator=g) * (4.0 / size)).to(dev).contiguous()
+    dout = torch.randn((n, 3, size, size), generator=g).to(dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    px = n * size * size
+    res = {}
+    for name in ("fwd", "bwd"):
+        times = []
+        for it in range(iters + 3):
+            flush.zero_()
+            gr = grid.clone().requires_grad_(name == "bwd")
+            im = img.clone().requires_grad_(name == "bwd")
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            if name == "fwd":
+                e0.record()
+                F.GridSampleFn.apply(gr, im, None)
+                e1.record()
+            else:
+                out = F.GridSampleFn.apply(gr, im, None)
+                dimg = torch.zeros_like(im)
+                dgrid = torch.empty_like(grid)
+                e0.record()
+                F.call("nemar_grid_sample_bwd", F.fptr(img), None, 1, n, 3, size, size, F.fptr(grid), size, size,
+                       F.fptr(dout), None, F.fptr(dimg), None, F.fptr(dgrid), F.stream())
+                e1.record()
+            torch.cuda.synchronize()
+            if it >= 3:
+                times.append(e0.elapsed_time(e1))
+        ms = sum(times) / len(times)
+        bpp = 32 if name == "fwd" else 52
+        gbs = px * bpp / (ms / 1e3) / 1e9
+        res[name] = {"gbs": round(gbs, 1), "frac_of_hbm_peak": round(gbs / peaks["hbm"], 4), "ms": round(ms, 4),
+                     "bytes_per_px": bpp}
+    res["config"] = "%dx%d, batch %d, C=3 fp32, grid = identity + N(0, 2 px); L2 flushed between launches" % (size, size, n)
+    res["peak_gbs"] = peaks["hbm"]
+    return res
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", type=str, default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=PER_GPU_BATCH, help="paired samples per GPU")
+    ap.add_argument("--size", type=int, default=HW)
+    ap.add_argument("--precision", type=str, default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--conv_engine", type=str, default="auto", choices=["auto", "generic"])
+    ap.add_argument("--no_cpu_baseline", action="store_true")
+    ap.add_argument("--kernel_timing", type=int, default=1, help="time conv launches with CUDA events (roofline)")
+    ap.add_argument("--grid_sample_bench", type=int, default=1)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_engine(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -99,7 +99,65 @@ def vptr(t):
     return C.c_void_p(t.data_ptr())
 
 
+COUNTERS = {"launches": 0}
+
+
+class KernelTimer:
+    """CUDA-event timing of the conv launches on the launching stream (bench.py's live roofline numbers)."""
+    CONV = {"nemar_conv2d_fprop": (0, 6, 4, 8), "nemar_conv2d_dgrad": (4, 0, 3, 5), "nemar_conv2d_wgrad": (0, 1, 2, 6)}
+
+    def __init__(self):
+        self.on = False
+        self.records = []
+
+    def enable(self, flag):
+        self.on = bool(flag)
+        self.records = []
+
+    def key_and_flops(self, name, args):
+        ix, iy, ig, itc = self.CONV[name]        # positions of: layer input side, output side, geometry, use_tc
+        x, y, g = args[ix], args[iy], args[ig]
+        pix = (x.n * x.h * x.w) if g.transposed else (y.n * y.h * y.w)
+        flops = 2.0 * pix * g.cin * g.cout * g.kh * g.kw
+        eng = "tc" if int(args[itc]) else "generic"
+        op = name.replace("nemar_conv2d_", "")
+        return "%s[%s]" % (op, eng), "%s[%s] %d->%d k%d s%d%s @%dx%d" % (
+            op, eng, g.cin, g.cout, g.kh, g.stride, "T" if g.transposed else "", y.h, y.w), flops
+
+    def collect(self):
+        """-> {kernel: {ms, n, flops, top: {geometry: ms}}} (synchronises)"""
+        if not self.records:
+            return {}
+        torch.cuda.synchronize()
+        out = {}
+        for key, geo, flops, e0, e1 in self.records:
+            ms = e0.elapsed_time(e1)
+            d = out.setdefault(key, {"ms": 0.0, "n": 0, "flops": 0.0, "top": {}})
+            d["ms"] += ms
+            d["n"] += 1
+            d["flops"] += flops
+            d["top"][geo] = d["top"].get(geo, 0.0) + ms
+        self.records = []
+        return out
+
+
+TIMER = KernelTimer()
+
+
 def call(name, *args):
+    COUNTERS["launches"] += 1
+    if TIMER.on and name in KernelTimer.CONV:
+        key, geo, flops = TIMER.key_and_flops(name, args)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        _call(name, *args)
+        e1.record()
+        TIMER.records.append((key, geo, flops, e0, e1))
+        return
+    _call(name, *args)
+
+
+def _call(name, *args):
     fn = getattr(lib(), name)
     conv = []
     for a in args:

@@ -1,0 +1,117 @@
+"""CPU-side checks: the C-ABI library builds, loads and exports every declared symbol; the host-side mirror
+of the reference's plugin surface (flags, registries, parameter trees, dataset dict) behaves; the N>1 gradient
+exchange works over gloo with world_size 2.  No CUDA compute is invoked here."""
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+from oracle import nemar_oracle as O
+from tests import helpers as H
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol(built_lib):
+    from nemar_b200.engine import lib
+    names = lib.declared_symbols()
+    assert len(names) >= 40
+    missing = [n for n in names if not hasattr(built_lib, n)]
+    assert not missing, "symbols declared in include/nemar_b200.h but not exported: %s" % missing
+    assert built_lib.nemar_version() == 100
+
+
+def test_bad_arguments_are_rejected_without_a_gpu(built_lib):
+    from nemar_b200.engine import lib
+    rc = built_lib.nemar_affine_grid_fwd(None, None, None, 0, 0, 0, None, None)
+    assert rc == -1 and b"affine_grid_fwd" in built_lib.nemar_last_error()
+    with pytest.raises(lib.EngineError):
+        lib.check(rc, "nemar_affine_grid_fwd")
+
+
+def test_no_cpu_fallback_in_product():
+    """The product must not import the oracle."""
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "nemar_b200")):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in src.replace("no CPU fallback", ""), "%s references the oracle" % f
+
+
+@pytest.mark.parametrize("case", ["c1_affine64", "c4_multires256"])
+def test_parameter_trees_match_reference_keys(case):
+    kw, batch, extra = H.CASE_FLAGS[case]
+    cfg = O.OracleConfig(**kw)
+    opt = H.engine_opt(cfg, batch, extra, gpu_ids="-1")
+    from nemar_b200.models import networks, stn
+    T = networks.define_G(3, 3, opt.ngf, opt.netG, opt.norm, False, opt.init_type, opt.init_gain, [])
+    D = networks.define_D(6, opt.ndf, opt.netD, 3, opt.norm, opt.init_type, opt.init_gain, [])
+    R = stn.define_stn(opt, opt.stn_type)
+    for net, shapes in ((T, O.resnet_generator_shapes(ngf=cfg.ngf, n_blocks=cfg.n_blocks)),
+                        (D, O.discriminator_shapes(ndf=cfg.ndf)),
+                        (R, O.affine_stn_shapes(height=cfg.height, width=cfg.width) if cfg.stn_type == "affine"
+                         else O.unet_stn_shapes())):
+        sd = net.state_dict()
+        assert list(sd.keys()) == list(shapes.keys())
+        assert all(tuple(sd[k].shape) == tuple(shapes[k]) for k in shapes)
+
+
+def test_init_statistics_follow_reference_quirks():
+    """down/1x1/refine convs ~ N(0,0.02) ('normal'); up convs fall back to kaiming (std ~0.047);
+    identity-init output conv ~ N(0,1e-5)."""
+    cfg = O.OracleConfig(stn_type="unet", height=256, width=256)
+    opt = H.engine_opt(cfg, 1, [], gpu_ids="-1")
+    from nemar_b200.models import stn
+    torch.manual_seed(0)
+    R = stn.define_stn(opt, "unet").state_dict()
+    assert abs(float(R["offset_map.down_2.conv_0.conv2d.weight"].std()) - 0.02) < 2e-3
+    assert abs(float(R["offset_map.up_3.conv2d.weight"].std()) - (2 / (1 + 0.04) / (128 * 9)) ** 0.5) < 3e-3
+    assert float(R["offset_map.output.conv2d.weight"].std()) < 2e-5
+
+
+def test_flags_and_registries():
+    from nemar_b200 import data, models
+    from nemar_b200.options.train_options import TrainOptions
+    opt = TrainOptions().parse(["--dataroot", "x", "--dataset_mode", "synthetic", "--gpu_ids", "-1", "--checkpoints_dir",
+                                "/tmp/nemar_b200_ckpt"], quiet=True)
+    assert (opt.model, opt.stn_type, opt.stn_cfg, opt.netG, opt.gan_mode, opt.lr, opt.beta1) == \
+        ("nemar", "affine", "A", "resnet_9blocks", "vanilla", 0.0002, 0.5)
+    assert (opt.img_height, opt.img_width, opt.lambda_recon, opt.lambda_GAN, opt.lambda_smooth, opt.multi_resolution) == \
+        (288, 384, 100.0, 1.0, 0.0, 1)
+    assert models.find_model_using_name("nemar").__name__ == "NEMARModel"
+    with pytest.raises(ModuleNotFoundError):
+        models.find_model_using_name("does_not_exist")
+    ds = data.create_dataset(opt)
+    item = ds.dataset[3]
+    assert set(item) == {"A", "B", "A_paths", "B_paths"} and item["A"].shape == (3, 288, 384)
+    assert float(item["A"].min()) >= -1 and float(item["A"].max()) <= 1
+    assert torch.equal(ds.dataset[3]["B"], item["B"])
+
+
+def test_gradient_bucket_allreduce_gloo_world2(tmp_path):
+    """N>1 path on CPU: two ranks, different shards, one all-reduce per bucket => identical averaged grads."""
+    script = tmp_path / "w.py"
+    script.write_text('''
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, %r)
+from nemar_b200.engine import parallel
+world, rank, _ = parallel.init_process_group_from_env("gloo")
+assert world == 2
+full = torch.arange(8.).view(4, 2)
+shard = parallel.shard_batch(full, rank, world)
+assert shard.shape[0] == 2 and float(shard[0, 0]) == 4.0 * rank
+bucket = torch.full((10,), float(rank + 1))
+hook = parallel.BucketAllReduce()
+scale = hook(bucket)
+assert scale == 0.5 and torch.allclose(bucket * scale, torch.full((10,), 1.5)) and hook.calls == 1
+dist.barrier()
+print("rank", rank, "ok")
+''' % ROOT)
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29533", str(script)], env=env,
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert r.stdout.count("ok") == 2
