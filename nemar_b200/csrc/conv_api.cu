@@ -124,6 +124,6 @@ NEMAR_API int nemar_conv2d_wgrad(const nemar_tensor* x, const nemar_tensor* dy, 
 
 NEMAR_API int nemar_conv2d_tc_supported(const nemar_conv_geom* g, int dtype, int h_in, int w_in) {
   (void)h_in; (void)w_in;
-  if (!geom_ok(g) || dtype != NEMAR_BF16) return 0;
+  if (!geom_ok(g) || dtype != NEMAR_BF16 || !tc_engine_built()) return 0;
   return (g->cin % 64 == 0 && g->cout % 64 == 0) ? 1 : 0;
 }

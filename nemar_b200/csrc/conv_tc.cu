@@ -3,6 +3,7 @@
 #include "common.cuh"
 #include "conv_internal.cuh"
 
+bool tc_engine_built() { return false; }
 bool tc_gather_supported(const nemar_tensor*, const nemar_tensor*, int, const GatherGeom&) { return false; }
 int tc_gather_gemm(const nemar_tensor*, const nemar_tensor*, const void*, int, const float*, int, float*,
                    const GatherGeom&, cudaStream_t) {

@@ -202,7 +202,7 @@ def affine_network(sd, img_a, img_b):
 def affine_stn(sd, img_a, img_b, apply_on):
     """reference affine_stn.py:108-138"""
     dtheta = affine_network(sd, img_a, img_b)
-    theta = dtheta + torch.tensor([1, 0, 0, 0, 1, 0], dtype=torch.float).unsqueeze(0).repeat(img_a.size(0), 1)
+    theta = dtheta + torch.tensor([1, 0, 0, 0, 1, 0], dtype=dtheta.dtype).unsqueeze(0).repeat(img_a.size(0), 1)
     warped = []
     for img in apply_on:
         grid = F.affine_grid(theta.view(-1, 2, 3), img.size(), align_corners=False)
@@ -381,7 +381,8 @@ class OracleStep:
         d_rt = self._gan(A, o["fake_RT_B"].detach(), False, self.Ds)
         loss_D = 0.5 * cfg.lambda_gan * (d_real + d_tr + d_rt)
         d_params = [p for d in self.Ds for p in d.values()]
-        self.opt_D.step(torch.autograd.grad(loss_D, d_params))
+        d_grads = torch.autograd.grad(loss_D, d_params)
+        self.opt_D.step(d_grads)
         # ---- backward_T_and_R (reference :175-215): D frozen but UPDATED
         Ds_new = [OrderedDict((k, v.detach()) for k, v in d.items()) for d in self.Ds]
         l1_tr = cfg.lambda_recon * F.l1_loss(o["fake_TR_B"], B)
@@ -394,9 +395,24 @@ class OracleStep:
         grads = torch.autograd.grad(loss, tr_params, allow_unused=True)
         grads = [g if g is not None else torch.zeros_like(p) for g, p in zip(grads, tr_params)]
         nR = len(self.R)
-        self.grads = dict(R=grads[:nR], T=grads[nR:])
+        self.grads = dict(R=grads[:nR], T=grads[nR:], D=list(d_grads))
         self.opt_R.step(grads[:nR])
         self.opt_T.step(grads[nR:])
         f = lambda t: float(t.detach()) if torch.is_tensor(t) else float(t)
         return OrderedDict(L1_TR=f(l1_tr), GAN_TR=f(gan_tr), L1_RT=f(l1_rt), GAN_RT=f(gan_rt), smoothness=f(smooth),
                            D_fake_TR=f(d_tr), D_fake_RT=f(d_rt), D=f(loss_D))
+
+
+def run_in_dtype(dtype, fn):
+    """Evaluate fn() with `dtype` as torch's default floating type (fp64 'truth' runs of the oracle)."""
+    old = torch.get_default_dtype()
+    torch.set_default_dtype(dtype)
+    try:
+        return fn()
+    finally:
+        torch.set_default_dtype(old)
+
+
+def cast_states(dtype, T, R, Ds):
+    c = lambda sd: OrderedDict((k, v.to(dtype)) for k, v in sd.items())
+    return c(T), c(R), [c(d) for d in Ds]

@@ -45,20 +45,27 @@ def test_unet_stn_forward_fp32_vs_oracle():
     assert abs(float(ereg) - float(reg)) < 2e-4 * max(1.0, abs(float(reg)))
 
 
+# Trajectories: the first step is pinned tightly.  Later steps are NOT reproducible to better than ~10-20 % even
+# between the oracle evaluated in fp32 and in fp64 (Adam's first updates are ~lr*sign(g), and the LSGAN gradient
+# through InstanceNorm is a cancellation-dominated quantity: fp32-vs-fp64 oracle D_fake_TR differs by 7 % at step 2
+# and 21 % at step 3 on c1 — measured, see DESIGN.md "Parity").  They are therefore checked loosely.
+LATER_RTOL, LATER_ATOL = 0.35, 0.1
+
+
+def _check_traj(losses, gold, first_rtol, first_atol):
+    np.testing.assert_allclose(losses[0], gold[0], rtol=first_rtol, atol=first_atol, err_msg="step-1 losses %s" % NAMES)
+    if len(losses) > 1:
+        np.testing.assert_allclose(losses[1:], gold[1:len(losses)], rtol=LATER_RTOL, atol=LATER_ATOL,
+                                   err_msg="later-step losses %s" % NAMES)
+
+
 @pytest.mark.parametrize("name,steps", [("c1_affine64", 3), ("c4_multires256", 2)])
 def test_training_step_fp32_vs_reference_golden(name, steps):
-    """Full optimize_parameters trajectories (fp32, generic engine) against the REFERENCE's own losses."""
+    """Full optimize_parameters (fp32, generic engine) against the REFERENCE's own logged losses."""
     g = np.load(os.path.join(GOLD, name + ".npz"))
     model, cfg, states, (A, B) = H.build_case(name)
     losses = np.array(H.run_engine_steps(model, A, B, steps))
-    np.testing.assert_allclose(losses, g["losses"][:steps], rtol=3e-3, atol=2e-4,
-                               err_msg="losses %s" % NAMES)
-    stride = int(g["img_stride"])
-    for tag, net in (("T", model.netT), ("R", model.netR), ("D", model.netD)):
-        sd = net.state_dict()
-        keep = np.array([k.endswith(".weight") for k in sd.keys()])
-        pabs = np.array([float(v.detach().double().abs().sum()) for v in sd.values()])
-        np.testing.assert_allclose(pabs[keep], g["pabs_" + tag][keep], rtol=2e-3, err_msg="updated weights of net" + tag)
+    _check_traj(losses, g["losses"], 3e-4, 2e-5)
 
 
 def test_first_step_images_fp32_vs_reference_golden():
@@ -77,7 +84,7 @@ def test_training_step_bf16_vs_reference_golden(name, steps, conv_engine):
     g = np.load(os.path.join(GOLD, name + ".npz"))
     model, cfg, states, (A, B) = H.build_case(name, precision="bf16", conv_engine=conv_engine)
     losses = np.array(H.run_engine_steps(model, A, B, steps))
-    np.testing.assert_allclose(losses, g["losses"][:steps], rtol=4e-2, atol=2e-2, err_msg="losses %s" % NAMES)
+    _check_traj(losses, g["losses"], 4e-2, 2e-2)
 
 
 def test_checkpoint_roundtrip_reference_keys(tmp_path):
@@ -88,3 +95,38 @@ def test_checkpoint_roundtrip_reference_keys(tmp_path):
     assert list(sd.keys()) == list(T.keys())
     assert all(torch.equal(sd[k], T[k]) for k in T)
     model.load_networks("latest")
+
+
+def _oracle_grads(cfg, T, R, Ds, A, B, dtype):
+    def go():
+        Tc, Rc, Dc = O.cast_states(dtype, T, R, Ds)
+        st = O.OracleStep(cfg, Tc, Rc, Dc)
+        st.step(A.to(dtype), B.to(dtype))
+        return {k: [g.double() for g in v] for k, v in st.grads.items()}
+    return O.run_in_dtype(dtype, go)
+
+
+@pytest.mark.parametrize("name,precision,factor,floor", [("c1_affine64", "fp32", 4.0, 1e-3), ("c4_multires256", "fp32", 4.0, 1e-3),
+                                                         ("c1_affine64", "bf16", 0.0, 0.35)])
+def test_gradients_vs_fp64_oracle(name, precision, factor, floor):
+    """Per-tensor weight gradients of both optimizer phases after one optimize_parameters.  Truth = the oracle in
+    fp64.  fp32 engine: error <= 4x the error the reference's own fp32 arithmetic (oracle fp32) makes, floor 1e-3.
+    bf16 engine: norm-wise error <= 35 % per tensor (bf16 has 8 mantissa bits and the LSGAN/InstanceNorm gradient
+    amplifies rounding ~1000x — the fp32 oracle itself is only good to 1e-2 here)."""
+    model, cfg, (T, R, Ds), (A, B) = H.build_case(name, precision=precision)
+    H.run_engine_steps(model, A, B, 1)
+    truth = _oracle_grads(cfg, T, R, Ds, A, B, torch.float64)
+    ref32 = _oracle_grads(cfg, T, R, Ds, A, B, torch.float32)
+    bad = []
+    for tag, net in (("R", model.netR), ("T", model.netT), ("D", model.netD)):
+        for i, (k, p) in enumerate(net.named_parameters()):
+            if not k.endswith(".weight"):
+                continue     # biases feeding an InstanceNorm have zero true gradient (rounding noise in any arithmetic)
+            t = truth[tag][i]
+            nrm = float(t.norm()) + 1e-30
+            e_eng = float((p.grad.detach().double().cpu() - t).norm()) / nrm
+            e_ref = float((ref32[tag][i] - t).norm()) / nrm
+            if e_eng > max(factor * e_ref, floor):
+                bad.append((e_eng, e_ref, tag, k))
+    msg = "\n".join("%s.%s engine err %.3e, fp32-oracle err %.3e" % (t, k, a, b) for a, b, t, k in sorted(bad, reverse=True)[:30])
+    assert not bad, "gradients less accurate than allowed (worst first):\n" + msg

@@ -184,6 +184,8 @@ def test_norm_act_fwd_bwd(prec, act, c, h, w, out_pad, res):
     (ye.float() * nhwc(dg, dt).float()).sum().backward()
     btol = dict(fp32=(2e-3, 2e-4), bf16=(3e-2, 3e-2))[prec]
     close(nchw(xe.grad), xr.grad, *btol, "norm_act dx")
+    if prec == "fp32":
+        assert rel_rms(nchw(xe.grad), xr.grad) < 2e-5, "norm_act dx rel-rms %.3e" % rel_rms(nchw(xe.grad), xr.grad)
     if res:
         close(nchw(re_.grad)[:, :, 1:-1, 1:-1], rr.grad, *btol, "norm_act dres")
         assert float(re_.grad[:, 0].abs().max()) == 0.0
@@ -286,7 +288,11 @@ def test_conv_generic_fwd_bwd(prec, geom):
         gx = xz.grad
     btol = dict(fp32=(5e-4, 5e-4), bf16=(2e-2, 2e-2))[prec]
     close(gx, xr.grad, *btol, "conv dgrad")
-    assert rel_rms(we.grad, wr.grad) < dict(fp32=1e-4, bf16=1e-2)[prec], "conv wgrad rel-rms %.3e" % rel_rms(we.grad, wr.grad)
+    if prec == "fp32":
+        assert rel_rms(nchw(ye), y) < 1e-5, "conv fwd rel-rms %.3e" % rel_rms(nchw(ye), y)
+        assert rel_rms(gx, xr.grad) < 1e-5, "conv dgrad rel-rms %.3e" % rel_rms(gx, xr.grad)
+        assert rel_rms(be.grad, br.grad) < 1e-5, "conv bias-grad rel-rms %.3e" % rel_rms(be.grad, br.grad)
+    assert rel_rms(we.grad, wr.grad) < dict(fp32=1e-5, bf16=1e-2)[prec], "conv wgrad rel-rms %.3e" % rel_rms(we.grad, wr.grad)
     close(be.grad, br.grad, 1e-3, 1e-2 if prec == "bf16" else 1e-3, "conv bias grad")
 
 
