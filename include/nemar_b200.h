@@ -71,6 +71,8 @@ int nemar_nhwc_to_nchw(const nemar_tensor* src, float* dst, int pad_mode, int ac
 int nemar_fill_channels(const nemar_tensor* t, int c0, int nc, void* stream);
 /* dst view <- src view (same n,h,w,c; any pads/slices); halo of dst filled per pad_mode */
 int nemar_copy_view(const nemar_tensor* src, const nemar_tensor* dst, int pad_mode, void* stream);
+/* dst view <- src view with a storage-dtype change (fp32 <-> bf16); same n,h,w,c; interiors only */
+int nemar_cast_view(const nemar_tensor* src, const nemar_tensor* dst, void* stream);
 /* dst view (=|+=) src view folded (adjoint of nemar_copy_view) */
 int nemar_copy_view_bwd(const nemar_tensor* dsrc_out, const nemar_tensor* ddst_in, int pad_mode,
                         int accumulate, void* stream);

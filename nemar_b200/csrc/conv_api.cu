@@ -2,6 +2,11 @@
 // Maps (operation, transposed) onto the two gather-GEMM modes and picks the engine (tcgen05 or generic).
 // Replaces nn.Conv2d / nn.ConvTranspose2d + autograd (models/networks.py:350,357,369-372,376,426,439,576,
 // 583,591,597; models/stn/layers.py:85).
+//
+// Channel padding: the geometry carries the REAL channel counts (the reference's weight shape); activation
+// tensors may carry more channels (x->c >= cin, y->c >= cout; the excess is zero) so that 3/6-channel images
+// and 1/2/3-channel heads fit the tensor-core tiles.  Packed weights are [y->c][taps][x->c] (forward pack) and
+// [x->c][taps][y->c] (backward pack) with zero padding; `bias` must hold y->c floats.
 #include "common.cuh"
 #include "conv_internal.cuh"
 
@@ -17,12 +22,12 @@ NEMAR_API int nemar_pack_weights(const float* w, const nemar_conv_geom* g, int d
   int rc = 0;
   if (!g->transposed) {
     // w[cout][cin][kh][kw]
-    if (wf) rc = generic_pack(w, wf, dtype, g->cout, g->cin, cin_p, g->kh, g->kw, /*w_is_oi=*/1, /*flip=*/0, s);
-    if (!rc && wd) rc = generic_pack(w, wd, dtype, g->cin, g->cout, cout_p, g->kh, g->kw, /*w_is_oi=*/0, /*flip=*/1, s);
+    if (wf) rc = generic_pack(w, wf, dtype, g->cout, cout_p, g->cin, cin_p, g->kh, g->kw, /*w_is_oi=*/1, /*flip=*/0, s);
+    if (!rc && wd) rc = generic_pack(w, wd, dtype, g->cin, cin_p, g->cout, cout_p, g->kh, g->kw, /*w_is_oi=*/0, /*flip=*/1, s);
   } else {
     // w[cin][cout][kh][kw]; forward pack [cout][taps][cin_p] flipped, backward pack [cin][taps][cout_p]
-    if (wf) rc = generic_pack(w, wf, dtype, g->cout, g->cin, cin_p, g->kh, g->kw, /*w_is_oi=*/0, /*flip=*/1, s);
-    if (!rc && wd) rc = generic_pack(w, wd, dtype, g->cin, g->cout, cout_p, g->kh, g->kw, /*w_is_oi=*/1, /*flip=*/0, s);
+    if (wf) rc = generic_pack(w, wf, dtype, g->cout, cout_p, g->cin, cin_p, g->kh, g->kw, /*w_is_oi=*/0, /*flip=*/1, s);
+    if (!rc && wd) rc = generic_pack(w, wd, dtype, g->cin, cin_p, g->cout, cout_p, g->kh, g->kw, /*w_is_oi=*/1, /*flip=*/0, s);
   }
   return rc;
 }
@@ -35,9 +40,10 @@ NEMAR_API int nemar_conv2d_fprop(const nemar_tensor* x, const void* w_packed, in
                                  const nemar_conv_geom* g, int act, const nemar_tensor* y, float* stats,
                                  int use_tc, void* stream) {
   NEMAR_REQUIRE(view_ok(x) && view_ok(y) && w_packed && geom_ok(g), "conv2d_fprop: bad args");
-  NEMAR_REQUIRE(x->c == g->cin && y->c == g->cout && x->n == y->n && w_cin_p >= g->cin &&
-                    (x->dtype == y->dtype || (!use_tc && y->dtype == NEMAR_F32)),
-                "conv2d_fprop: channel/dtype mismatch (weights share x's dtype; y may be fp32 on the generic engine)");
+  NEMAR_REQUIRE(x->c >= g->cin && y->c >= g->cout && x->n == y->n && w_cin_p == x->c &&
+                    (x->dtype == y->dtype || y->dtype == NEMAR_F32),
+                "conv2d_fprop: channel/dtype mismatch (weights are packed for x->c input channels and share x's "
+                "dtype; y may be fp32)");
   NEMAR_REQUIRE(y->pad == 0, "conv2d_fprop: output must not carry a halo");
   cudaStream_t s = (cudaStream_t)stream;
   GatherGeom gg;
@@ -53,16 +59,12 @@ NEMAR_API int nemar_conv2d_fprop(const nemar_tensor* x, const void* w_packed, in
                   "conv2d_fprop(transposed): bad output extent");
     gg.sm = 1; gg.sd = g->stride; gg.pe = g->kh - 1 - g->pad;
   }
-  int rc;
-  if (use_tc) {
-    NEMAR_REQUIRE(tc_gather_supported(x, y, w_cin_p, gg), "conv2d_fprop: geometry not supported by the tcgen05 engine");
-    rc = tc_gather_gemm(x, y, w_packed, w_cin_p, bias, act, stats, gg, s);
-  } else {
-    rc = generic_gather_gemm(x, y, w_packed, x->dtype, w_cin_p, bias, act, gg, s);
-    if (!rc && stats) {
-      NEMAR_REQUIRE(act == NEMAR_ACT_NONE, "conv2d_fprop: stats need the pre-activation output");
-      rc = nemar_instnorm_stats(y, stats, stream);
-    }
+  if (use_tc && tc_gather_supported(x, y, w_cin_p, gg))   // otherwise: CUDA-core engine (still on the GPU)
+    return tc_gather_gemm(x, y, w_packed, w_cin_p, bias, act, stats, gg, s);
+  int rc = generic_gather_gemm(x, y, w_packed, x->dtype, w_cin_p, bias, act, gg, s);
+  if (!rc && stats) {
+    NEMAR_REQUIRE(act == NEMAR_ACT_NONE, "conv2d_fprop: stats need the pre-activation output");
+    rc = nemar_instnorm_stats(y, stats, stream);
   }
   return rc;
 }
@@ -70,9 +72,9 @@ NEMAR_API int nemar_conv2d_fprop(const nemar_tensor* x, const void* w_packed, in
 NEMAR_API int nemar_conv2d_dgrad(const nemar_tensor* dy, const void* w_packed_d, int w_cout_p,
                                  const nemar_conv_geom* g, const nemar_tensor* dx, int use_tc, void* stream) {
   NEMAR_REQUIRE(view_ok(dy) && view_ok(dx) && w_packed_d && geom_ok(g), "conv2d_dgrad: bad args");
-  NEMAR_REQUIRE(dy->c == g->cout && dx->c == g->cin && dx->n == dy->n && w_cout_p >= g->cout && dy->pad == 0 &&
-                    (dx->dtype == dy->dtype || (!use_tc && dy->dtype == NEMAR_F32)),
-                "conv2d_dgrad: channel/dtype mismatch (weights share dx's dtype; dy may be fp32 on the generic engine)");
+  NEMAR_REQUIRE(dy->c >= g->cout && dx->c >= g->cin && dx->n == dy->n && w_cout_p == dy->c && dy->pad == 0 &&
+                    (dx->dtype == dy->dtype || dy->dtype == NEMAR_F32),
+                "conv2d_dgrad: channel/dtype mismatch (weights are packed for dy->c channels and share dx's dtype)");
   cudaStream_t s = (cudaStream_t)stream;
   GatherGeom gg;
   gg.kh = g->kh; gg.kw = g->kw;
@@ -83,47 +85,48 @@ NEMAR_API int nemar_conv2d_dgrad(const nemar_tensor* dy, const void* w_packed_d,
     NEMAR_REQUIRE(dx->pad == 0, "conv2d_dgrad(transposed): halo not supported");
     gg.sm = g->stride; gg.sd = 1; gg.pe = g->pad; gg.dst_padded = 0;
   }
-  if (use_tc) {
-    NEMAR_REQUIRE(tc_gather_supported(dy, dx, w_cout_p, gg), "conv2d_dgrad: geometry not supported by the tcgen05 engine");
+  if (use_tc && tc_gather_supported(dy, dx, w_cout_p, gg))
     return tc_gather_gemm(dy, dx, w_packed_d, w_cout_p, nullptr, NEMAR_ACT_NONE, nullptr, gg, s);
-  }
   return generic_gather_gemm(dy, dx, w_packed_d, dx->dtype, w_cout_p, nullptr, NEMAR_ACT_NONE, gg, s);
 }
 
 // conv-view of a weight-gradient problem: for ConvTranspose2d the roles of x and dy swap.
-static void wgrad_view(const nemar_tensor* x, const nemar_tensor* dy, const nemar_conv_geom* g,
-                       const nemar_tensor** xc, const nemar_tensor** dyc, int* pe) {
-  if (!g->transposed) { *xc = x; *dyc = dy; *pe = g->pad - x->pad; }
-  else { *xc = dy; *dyc = x; *pe = g->pad - dy->pad; }
+struct WgradView {
+  const nemar_tensor *xc, *dyc;
+  int pe, co_real, ci_real;
+};
+static WgradView wgrad_view(const nemar_tensor* x, const nemar_tensor* dy, const nemar_conv_geom* g) {
+  WgradView v;
+  if (!g->transposed) { v.xc = x; v.dyc = dy; v.pe = g->pad - x->pad; v.co_real = g->cout; v.ci_real = g->cin; }
+  else { v.xc = dy; v.dyc = x; v.pe = g->pad - dy->pad; v.co_real = g->cin; v.ci_real = g->cout; }
+  return v;
 }
 
 NEMAR_API int64_t nemar_conv2d_wgrad_workspace(const nemar_tensor* x, const nemar_tensor* dy,
                                                const nemar_conv_geom* g, int use_tc) {
   if (!use_tc || !view_ok(x) || !view_ok(dy) || !geom_ok(g)) return 0;
-  const nemar_tensor *xc, *dyc; int pe;
-  wgrad_view(x, dy, g, &xc, &dyc, &pe);
-  return tc_wgrad_workspace(xc, dyc, g->kh, g->kw, g->stride, pe);
+  WgradView v = wgrad_view(x, dy, g);
+  return tc_wgrad_workspace(v.xc, v.dyc, g->kh, g->kw, g->stride, v.pe);
 }
 
 NEMAR_API int nemar_conv2d_wgrad(const nemar_tensor* x, const nemar_tensor* dy, const nemar_conv_geom* g,
                                  float* dw, void* workspace, int64_t workspace_bytes, int use_tc, void* stream) {
   NEMAR_REQUIRE(view_ok(x) && view_ok(dy) && dw && geom_ok(g), "conv2d_wgrad: bad args");
-  NEMAR_REQUIRE(x->c == g->cin && dy->c == g->cout && x->n == dy->n && (x->dtype == dy->dtype || !use_tc),
-                "conv2d_wgrad: channel/dtype mismatch");
-  const nemar_tensor *xc, *dyc; int pe;
-  wgrad_view(x, dy, g, &xc, &dyc, &pe);
-  NEMAR_REQUIRE(dyc->pad == 0 && pe >= 0, "conv2d_wgrad: unsupported halo configuration");
+  NEMAR_REQUIRE(x->c >= g->cin && dy->c >= g->cout && x->n == dy->n, "conv2d_wgrad: channel mismatch");
+  WgradView v = wgrad_view(x, dy, g);
+  NEMAR_REQUIRE(v.dyc->pad == 0 && v.pe >= 0, "conv2d_wgrad: unsupported halo configuration");
   cudaStream_t s = (cudaStream_t)stream;
-  if (use_tc) {
-    NEMAR_REQUIRE(tc_wgrad_supported(xc, dyc, g->kh, g->kw, g->stride, pe),
-                  "conv2d_wgrad: geometry not supported by the tcgen05 engine");
-    return tc_wgrad(xc, dyc, dw, g->kh, g->kw, g->stride, pe, workspace, workspace_bytes, s);
-  }
-  return generic_wgrad(xc, dyc, dw, g->kh, g->kw, g->stride, pe, s);
+  if (use_tc && tc_wgrad_supported(v.xc, v.dyc, g->kh, g->kw, g->stride, v.pe))
+    return tc_wgrad(v.xc, v.dyc, dw, v.co_real, v.ci_real, g->kh, g->kw, g->stride, v.pe, workspace, workspace_bytes, s);
+  // generic engine: narrow the views to the real channels (the padding holds zeros and contributes nothing)
+  nemar_tensor xr = *v.xc, dr = *v.dyc;
+  xr.c = v.ci_real; dr.c = v.co_real;
+  return generic_wgrad(&xr, &dr, dw, g->kh, g->kw, g->stride, v.pe, s);
 }
 
 NEMAR_API int nemar_conv2d_tc_supported(const nemar_conv_geom* g, int dtype, int h_in, int w_in) {
   (void)h_in; (void)w_in;
   if (!geom_ok(g) || dtype != NEMAR_BF16 || !tc_engine_built()) return 0;
-  return (g->cin % 64 == 0 && g->cout % 64 == 0) ? 1 : 0;
+  if (!(g->stride == 1 || g->stride == 2) || g->kh * g->kw > 49) return 0;
+  return 1;   // any channel count: the host pads activations/weights to a multiple of 16
 }

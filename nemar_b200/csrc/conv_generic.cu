@@ -196,11 +196,11 @@ wgrad_kernel(TView x, TView dy, float* __restrict__ dw, int kh, int kw, int stri
 }
 
 // ---- weight packing --------------------------------------------------------------------------
-// out[o][a][b][i] (i padded to ip) = w[(o,i) or (i,o)][a or KH-1-a][b or KW-1-b]
+// out[o][a][b][i] (o padded to op, i padded to ip; padding is zero) = w[(o,i) or (i,o)][a or KH-1-a][b or KW-1-b]
 template <typename T>
-__global__ void pack_kernel(const float* __restrict__ w, T* __restrict__ out, int O, int I, int ip, int kh,
+__global__ void pack_kernel(const float* __restrict__ w, T* __restrict__ out, int O, int op, int I, int ip, int kh,
                             int kw, int w_is_oi /* w indexed [o][i] else [i][o] */, int flip) {
-  const int64_t total = (int64_t)O * kh * kw * ip;
+  const int64_t total = (int64_t)op * kh * kw * ip;
   for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
        idx += (int64_t)gridDim.x * blockDim.x) {
     int i = (int)(idx % ip);
@@ -209,7 +209,7 @@ __global__ void pack_kernel(const float* __restrict__ w, T* __restrict__ out, in
     int a = (int)(r % kh);
     int o = (int)(r / kh);
     float v = 0.f;
-    if (i < I) {
+    if (i < I && o < O) {
       int aa = flip ? kh - 1 - a : a, bb = flip ? kw - 1 - b : b;
       int64_t widx = w_is_oi ? (((int64_t)o * I + i) * kh + aa) * kw + bb
                              : (((int64_t)i * O + o) * kh + aa) * kw + bb;
@@ -254,10 +254,10 @@ int generic_wgrad(const nemar_tensor* x, const nemar_tensor* dy, float* dw, int 
   return 0;
 }
 
-int generic_pack(const float* w, void* out, int dtype, int O, int I, int ip, int kh, int kw, int w_is_oi,
+int generic_pack(const float* w, void* out, int dtype, int O, int op, int I, int ip, int kh, int kw, int w_is_oi,
                  int flip, cudaStream_t s) {
-  int64_t total = (int64_t)O * kh * kw * ip;
-  DISPATCH_DTYPE(dtype, T, (pack_kernel<T><<<grid_for(total, 256), 256, 0, s>>>(w, (T*)out, O, I, ip, kh, kw,
+  int64_t total = (int64_t)op * kh * kw * ip;
+  DISPATCH_DTYPE(dtype, T, (pack_kernel<T><<<grid_for(total, 256), 256, 0, s>>>(w, (T*)out, O, op, I, ip, kh, kw,
                                                                                  w_is_oi, flip)));
   NEMAR_LAUNCH_CHECK();
   return 0;

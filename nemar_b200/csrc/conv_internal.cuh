@@ -15,7 +15,7 @@ int generic_gather_gemm(const nemar_tensor* src, const nemar_tensor* dst, const 
                         const float* bias, int act, const GatherGeom& gg, cudaStream_t s);
 int generic_wgrad(const nemar_tensor* x, const nemar_tensor* dy, float* dw, int kh, int kw, int stride, int pe,
                   cudaStream_t s);
-int generic_pack(const float* w, void* out, int dtype, int O, int I, int ip, int kh, int kw, int w_is_oi,
+int generic_pack(const float* w, void* out, int dtype, int O, int op, int I, int ip, int kh, int kw, int w_is_oi,
                  int flip, cudaStream_t s);
 
 // tcgen05 / TMA engine — conv_tc.cu
@@ -25,5 +25,5 @@ int tc_gather_gemm(const nemar_tensor* src, const nemar_tensor* dst, const void*
                    const float* bias, int act, float* stats, const GatherGeom& gg, cudaStream_t s);
 bool tc_wgrad_supported(const nemar_tensor* x, const nemar_tensor* dy, int kh, int kw, int stride, int pe);
 int64_t tc_wgrad_workspace(const nemar_tensor* x, const nemar_tensor* dy, int kh, int kw, int stride, int pe);
-int tc_wgrad(const nemar_tensor* x, const nemar_tensor* dy, float* dw, int kh, int kw, int stride, int pe,
-             void* workspace, int64_t workspace_bytes, cudaStream_t s);
+int tc_wgrad(const nemar_tensor* x, const nemar_tensor* dy, float* dw, int co_real, int ci_real, int kh, int kw, int stride,
+             int pe, void* workspace, int64_t workspace_bytes, cudaStream_t s);

@@ -4,12 +4,14 @@
 //  gather kernel (Conv2d fprop, Conv2d dgrad, ConvTranspose2d fprop/dgrad):
 //      D[pixel][c_out] = sum_{tap, c_in} SRC[pixel @ tap][c_in] * Wp[c_out][tap][c_in]
 //    M = 128 destination pixels (a TW x TH x TN box of one or more images), N = BN channels, K = taps * C_in.
-//    A tiles are fetched by ONE 4-D TMA box per (tap, 64-channel chunk): the box start is shifted by the tap
+//    A tiles are fetched by ONE 4-D TMA box per (tap, BK-channel chunk): the box start is shifted by the tap
 //    offset, out-of-bounds rows are zero-filled by TMA (zero padding and tile overhang for free), reflect halos
 //    are materialised by the producer pass so they are ordinary data, stride-2 convolutions use the TMA
 //    traversal stride, and stride-2 data gradients / transposed convolutions are decomposed into the four
 //    output-parity classes, each a stride-1 gather over a subset of taps.  Both operands land in shared memory
-//    in the canonical K-major SWIZZLE_128B layout consumed directly by tcgen05.mma (cta_group::1, M=128).
+//    in the canonical K-major swizzled layout consumed directly by tcgen05.mma (cta_group::1, M=128).
+//    BK = 64 / 32 / 16 channels per k-step (SWIZZLE_128B / 64B / 32B) covers every channel count of the path:
+//    256/128/64, the 32- and 96-channel full-resolution STN layers, and 3/6-channel images padded to 16.
 //
 //  wgrad kernel:  dW[c_out][tap][c_in] = sum_pixels dY[pixel][c_out] * X[pixel @ tap][c_in]
 //    M = 128 output channels, N = BN input channels, K = pixels; both operands are the same NHWC boxes, used
@@ -29,9 +31,17 @@ using namespace tc;
 namespace {
 
 constexpr int BM = 128;         // UMMA M (TMEM lanes)
-constexpr int BK = 64;          // bf16 elements per k-step = one 128-byte swizzle row
 constexpr int MAX_TAPS = 49;
 constexpr int NTHREADS = 192;
+
+__host__ __device__ constexpr uint32_t round1k(uint32_t v) { return (v + 1023u) & ~1023u; }
+__host__ __device__ constexpr uint64_t layout_for(int chunk_elems) {
+  return chunk_elems == 64 ? LAYOUT_SW128 : (chunk_elems == 32 ? LAYOUT_SW64 : LAYOUT_SW32);
+}
+static CUtensorMapSwizzle swizzle_for(int chunk_elems) {
+  return chunk_elems == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (chunk_elems == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+}
+static int chunk_for(int c) { return (c % 64 == 0) ? 64 : ((c % 32 == 0) ? 32 : 16); }
 
 // -------------------------------------------------------------------------------------------------
 // driver entry point for tensor-map encoding (no link-time dependency on libcuda)
@@ -63,22 +73,22 @@ static int make_act_map(CUtensorMap* m, const nemar_tensor* t, int box_c, int bx
   cuuint32_t estr[4] = {1, (cuuint32_t)es, (cuuint32_t)es, 1};
   void* base = (char*)t->ptr + (size_t)t->coff * 2;
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   swizzle_for(box_c), CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   NEMAR_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(activation) failed: %d (c=%d cs=%d wp=%d hp=%d n=%d box=%d,%d,%d,%d es=%d)",
                 (int)r, t->c, t->cs, wp, hp, t->n, box_c, bx, by, bn, es);
   return 0;
 }
 
-// 2-D weight map: rows = output channels, K contiguous
-static int make_w_map(CUtensorMap* m, const void* w, int rows, int k_total, int box_rows) {
+// 2-D weight map: rows = output channels, K contiguous; box (bk, box_rows)
+static int make_w_map(CUtensorMap* m, const void* w, int rows, int k_total, int bk, int box_rows) {
   EncodeTiledFn enc = get_encode();
   NEMAR_REQUIRE(enc, "cuTensorMapEncodeTiled unavailable");
   cuuint64_t dims[2] = {(cuuint64_t)k_total, (cuuint64_t)rows};
   cuuint64_t strides[1] = {(cuuint64_t)k_total * 2};
-  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+  cuuint32_t box[2] = {(cuuint32_t)bk, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)w, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   swizzle_for(bk), CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   NEMAR_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(weights) failed: %d", (int)r);
   return 0;
 }
@@ -96,26 +106,37 @@ struct GatherParams {
   int dw, dh, dn;                // extent of the destination index space covered by this launch
   int ostep, oy0, ox0;           // destination coordinate = t * ostep + o0  (parity classes)
   long long ds_n, ds_y, ds_x;    // destination strides (elements)
-  __nv_bfloat16* dst;            // destination base (channel offset applied)
+  void* dst;                     // destination base (channel offset applied); bf16 or fp32
   int cd;                        // destination channels
   const float* bias;
   int act;
 };
 
-template <int BN, int STAGES>
+template <int BN, int BK>
+struct GatherCfg {
+  static constexpr uint32_t A_BYTES = round1k(BM * BK * 2), B_BYTES = round1k(BN * BK * 2);
+  static constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES_RAW = (int)(98304u / STAGE_BYTES);
+  static constexpr int STAGES = STAGES_RAW > 8 ? 8 : (STAGES_RAW < 2 ? 2 : STAGES_RAW);
+  static constexpr uint32_t TX_BYTES = BM * BK * 2 + BN * BK * 2;
+  static constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
+  static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + 1024 + 256;
+};
+
+template <int BN, int BK, bool F32OUT>
 __global__ void __launch_bounds__(NTHREADS)
 tc_gather_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ GatherParams P) {
-  constexpr uint32_t A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
+  using Cfg = GatherCfg<BN, BK>;
+  constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  uint64_t* full_bar = (uint64_t*)(smem + STAGES * STAGE_BYTES);
+  uint64_t* full_bar = (uint64_t*)(smem + STAGES * Cfg::STAGE_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full = empty_bar + STAGES;
   uint32_t* tmem_slot = (uint32_t*)(tmem_full + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  // tile coordinates
   int t = blockIdx.x;
   const int tx = t % P.tiles_x; t /= P.tiles_x;
   const int ty = t % P.tiles_y;
@@ -131,7 +152,7 @@ tc_gather_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     mbar_init(tmem_full, 1);
     fence_mbar_init();
   }
-  if (warp == 2) tmem_alloc(tmem_slot, BN);
+  if (warp == 2) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -144,10 +165,10 @@ tc_gather_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       for (int ks = 0; ks < ksteps; ++ks) {
         const int tap = ks / P.kchunks, kc = ks - tap * P.kchunks;
         mbar_wait(&empty_bar[stage], phase ^ 1);
-        uint8_t* sa = smem + stage * STAGE_BYTES;
-        mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
+        uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+        mbar_expect_tx(&full_bar[stage], Cfg::TX_BYTES);
         tma_load_4d(sa, &tmA, &full_bar[stage], kc * BK, x0 * P.sm + P.tdx[tap], y0 * P.sm + P.tdy[tap], n0);
-        tma_load_2d(sa + A_BYTES, &tmB, &full_bar[stage], P.twi[tap] * P.cs + kc * BK, c0);
+        tma_load_2d(sa + Cfg::A_BYTES, &tmB, &full_bar[stage], P.twi[tap] * P.cs + kc * BK, c0);
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
@@ -155,15 +176,16 @@ tc_gather_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (lane == 0) {
       // ===== MMA issuer =====
       constexpr uint32_t idesc = make_idesc_bf16(BM, BN, 0, 0);
+      constexpr uint32_t SBO = 8 * BK * 2;     // 8 rows of one swizzle atom
       int stage = 0; uint32_t phase = 0;
       for (int ks = 0; ks < ksteps; ++ks) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
-        const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
-        const uint64_t adesc = make_smem_desc(sa, 16, 1024, LAYOUT_SW128);
-        const uint64_t bdesc = make_smem_desc(sa + A_BYTES, 16, 1024, LAYOUT_SW128);
+        const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+        const uint64_t adesc = make_smem_desc(sa, 16, SBO, layout_for(BK));
+        const uint64_t bdesc = make_smem_desc(sa + Cfg::A_BYTES, 16, SBO, layout_for(BK));
 #pragma unroll
-        for (int k = 0; k < BK / 16; ++k)   // +32 bytes per UMMA_K inside the 128-byte swizzle row
+        for (int k = 0; k < BK / 16; ++k)   // +32 bytes per UMMA_K inside the swizzled row
           umma_bf16(tmem_base, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (ks > 0 || k > 0) ? 1u : 0u);
         umma_commit(&empty_bar[stage]);
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -177,29 +199,35 @@ tc_gather_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int rx = row % P.tw, ry = (row / P.tw) % P.th, rn = row / (P.tw * P.th);
     const int px = x0 + rx, py = y0 + ry, pn = n0 + rn;
     const bool valid = px < P.dw && py < P.dh && pn < P.dn;
-    __nv_bfloat16* out = P.dst + (long long)pn * P.ds_n + (long long)(py * P.ostep + P.oy0) * P.ds_y +
-                         (long long)(px * P.ostep + P.ox0) * P.ds_x + c0;
+    const long long off = (long long)pn * P.ds_n + (long long)(py * P.ostep + P.oy0) * P.ds_y +
+                          (long long)(px * P.ostep + P.ox0) * P.ds_x + c0;
     mbar_wait(tmem_full, 0);
     tc_fence_after();
 #pragma unroll 1
-    for (int cc = 0; cc < BN; cc += 32) {
+    for (int cc = 0; cc < (int)Cfg::TMEM_COLS; cc += 32) {
       float v[32];
       tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)cc, v);
       if (valid) {
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
-          if (c0 + cc + g * 8 < P.cd) {
+          if (cc + g * 8 < BN && c0 + cc + g * 8 < P.cd) {
             float f[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
               float b = P.bias ? __ldg(P.bias + c0 + cc + g * 8 + j) : 0.f;
               f[j] = act_fwd(v[g * 8 + j] + b, P.act);
             }
-            uint4 pk;
-            __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&pk);
+            if constexpr (F32OUT) {
+              float* o = (float*)P.dst + off + cc + g * 8;
+              *reinterpret_cast<float4*>(o) = make_float4(f[0], f[1], f[2], f[3]);
+              *reinterpret_cast<float4*>(o + 4) = make_float4(f[4], f[5], f[6], f[7]);
+            } else {
+              uint4 pk;
+              __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&pk);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) h[j] = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
-            *reinterpret_cast<uint4*>(out + cc + g * 8) = pk;
+              for (int j = 0; j < 4; ++j) h[j] = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+              *reinterpret_cast<uint4*>((__nv_bfloat16*)P.dst + off + cc + g * 8) = pk;
+            }
           }
         }
       }
@@ -209,49 +237,58 @@ tc_gather_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, BN);
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
   }
 }
 
-static size_t gather_smem_bytes(int BN, int stages) {
-  return (size_t)stages * (BM * BK * 2 + (size_t)BN * BK * 2) + 1024 + 256;
-}
-
-static void pick_tile(int dw, int dh, int dn, int& tw, int& th, int& tn) {
+static void pick_tile(int dw, int dh, int& tw, int& th, int& tn, int total) {
   tw = 1;
-  while (tw < dw && tw < 128) tw <<= 1;
+  while (tw < dw && tw < total) tw <<= 1;
   th = 1;
-  while (th < dh && tw * th < 128) th <<= 1;
-  tn = 128 / (tw * th);
-  (void)dn;
+  while (th < dh && tw * th < total) th <<= 1;
+  tn = total / (tw * th);
 }
 
-template <int BN>
-static int launch_gather(const CUtensorMap& tmA, const CUtensorMap& tmB, const GatherParams& P, int ctiles, cudaStream_t s) {
-  constexpr int STAGES = (BN == 128) ? 3 : 4;
-  size_t smem = gather_smem_bytes(BN, STAGES);
+template <int BN, int BK, bool F32OUT>
+static int launch_gather_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const GatherParams& P, int ctiles, cudaStream_t s) {
+  using Cfg = GatherCfg<BN, BK>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(tc_gather_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(tc_gather_kernel<BN, BK, F32OUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
     NEMAR_REQUIRE(e == cudaSuccess, "cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
     attr_set = true;
   }
   dim3 grid((unsigned)(P.tiles_x * P.tiles_y * P.tiles_n), (unsigned)ctiles);
-  tc_gather_kernel<BN, STAGES><<<grid, NTHREADS, smem, s>>>(tmA, tmB, P);
+  tc_gather_kernel<BN, BK, F32OUT><<<grid, NTHREADS, Cfg::SMEM, s>>>(tmA, tmB, P);
   NEMAR_LAUNCH_CHECK();
   return 0;
 }
 
-static bool tc_view_ok(const nemar_tensor* t) {
-  return t->dtype == NEMAR_BF16 && t->c % 64 == 0 && t->cs % 8 == 0 && t->coff % 8 == 0 && ((((uintptr_t)t->ptr) & 15) == 0);
+template <int BN, int BK>
+static int launch_gather_f(const CUtensorMap& a, const CUtensorMap& b, const GatherParams& P, int ct, bool f32, cudaStream_t s) {
+  return f32 ? launch_gather_t<BN, BK, true>(a, b, P, ct, s) : launch_gather_t<BN, BK, false>(a, b, P, ct, s);
 }
+
+template <int BN>
+static int launch_gather_k(const CUtensorMap& a, const CUtensorMap& b, const GatherParams& P, int ct, int bk, bool f32, cudaStream_t s) {
+  if (bk == 64) return launch_gather_f<BN, 64>(a, b, P, ct, f32, s);
+  if (bk == 32) return launch_gather_f<BN, 32>(a, b, P, ct, f32, s);
+  return launch_gather_f<BN, 16>(a, b, P, ct, f32, s);
+}
+
+static bool tc_view_ok(const nemar_tensor* t, bool allow_f32) {
+  const bool dt_ok = t->dtype == NEMAR_BF16 || (allow_f32 && t->dtype == NEMAR_F32);
+  return dt_ok && t->c % 16 == 0 && t->cs % 8 == 0 && t->coff % 8 == 0 && ((((uintptr_t)t->ptr) & 15) == 0);
+}
+
+static int gather_bn(int cd) { return (cd % 128 == 0) ? 128 : ((cd % 64 == 0) ? 64 : ((cd % 32 == 0) ? 32 : 16)); }
 
 }  // namespace
 
 bool tc_engine_built() { return true; }
 
 bool tc_gather_supported(const nemar_tensor* src, const nemar_tensor* dst, int wp_cs, const GatherGeom& gg) {
-  if (!tc_view_ok(src) || !tc_view_ok(dst)) return false;
+  if (!tc_view_ok(src, false) || !tc_view_ok(dst, true)) return false;
   if (wp_cs != src->c) return false;
   if (gg.kh * gg.kw > MAX_TAPS) return false;
   if (!((gg.sm == 1 || gg.sm == 2) && (gg.sd == 1 || gg.sd == 2)) || (gg.sm == 2 && gg.sd == 2)) return false;
@@ -267,10 +304,13 @@ int tc_gather_gemm(const nemar_tensor* src_in, const nemar_tensor* dst_in, const
   nemar_tensor src = *src_in, dst = *dst_in;
   src.h += 2 * src.pad; src.w += 2 * src.pad; src.pad = 0;
   dst.h += 2 * dst.pad; dst.w += 2 * dst.pad; dst.pad = 0;
-  const int BN = (dst.c % 128 == 0) ? 128 : 64;
+  const int BN = gather_bn(dst.c);
+  const int BK = chunk_for(src.c);
+  const bool f32 = dst.dtype == NEMAR_F32;
+  const int esz = f32 ? 4 : 2;
   const int taps_total = gg.kh * gg.kw;
   CUtensorMap tmB;
-  int rc = make_w_map(&tmB, wp, dst.c, taps_total * src.c, BN);
+  int rc = make_w_map(&tmB, wp, dst.c, taps_total * src.c, BK, BN);
   if (rc) return rc;
 
   const int nclass = (gg.sd == 2) ? 4 : 1;
@@ -296,19 +336,16 @@ int tc_gather_gemm(const nemar_tensor* src_in, const nemar_tensor* dst_in, const
     P.dw = (gg.sd == 2) ? (dst.w - pxc + 1) / 2 : dst.w;
     P.dn = dst.n;
     if (P.dh <= 0 || P.dw <= 0) continue;
-    if (P.ntaps == 0) {
-      // a parity class no tap reaches (possible only for k < stride): its outputs are bias-only; not on the path
-      NEMAR_REQUIRE(false, "tc_gather_gemm: parity class without taps");
-    }
+    NEMAR_REQUIRE(P.ntaps > 0, "tc_gather_gemm: parity class without taps");
     P.kchunks = src.c / BK;
     P.cs = src.c;
-    pick_tile(P.dw, P.dh, P.dn, P.tw, P.th, P.tn);
+    pick_tile(P.dw, P.dh, P.tw, P.th, P.tn, BM);
     P.tiles_x = (P.dw + P.tw - 1) / P.tw;
     P.tiles_y = (P.dh + P.th - 1) / P.th;
     P.tiles_n = (P.dn + P.tn - 1) / P.tn;
     P.sm = gg.sm;
     P.ds_x = dst.cs; P.ds_y = (long long)dst.w * dst.cs; P.ds_n = (long long)dst.h * dst.w * dst.cs;
-    P.dst = (__nv_bfloat16*)dst.ptr + dst.coff;
+    P.dst = (char*)dst.ptr + (size_t)dst.coff * esz;
     P.cd = dst.c;
     P.bias = bias;
     P.act = act;
@@ -316,7 +353,12 @@ int tc_gather_gemm(const nemar_tensor* src_in, const nemar_tensor* dst_in, const
     rc = make_act_map(&tmA, &src, BK, P.tw, P.th, P.tn, gg.sm);
     if (rc) return rc;
     const int ctiles = (dst.c + BN - 1) / BN;
-    rc = (BN == 128) ? launch_gather<128>(tmA, tmB, P, ctiles, s) : launch_gather<64>(tmA, tmB, P, ctiles, s);
+    switch (BN) {
+      case 128: rc = launch_gather_k<128>(tmA, tmB, P, ctiles, BK, f32, s); break;
+      case 64: rc = launch_gather_k<64>(tmA, tmB, P, ctiles, BK, f32, s); break;
+      case 32: rc = launch_gather_k<32>(tmA, tmB, P, ctiles, BK, f32, s); break;
+      default: rc = launch_gather_k<16>(tmA, tmB, P, ctiles, BK, f32, s); break;
+    }
     if (rc) return rc;
   }
   if (stats) {
@@ -331,30 +373,39 @@ int tc_gather_gemm(const nemar_tensor* src_in, const nemar_tensor* dst_in, const
 // =================================================================================================
 namespace {
 
-constexpr int WG_KP = 64;     // pixels per k-step (box of kw x kh x kn pixels)
+constexpr int WG_KP = 64;     // pixels per k-step (box of tw x th x tn pixels)
 
 struct WgradParams {
   int tw, th, tn;                 // pixel box (tw*th*tn == 64)
   int tiles_x, tiles_y, tiles_n;  // pixel tiles over dy
   int tiles_per_split;            // pixel tiles handled by one CTA
-  int stride;                     // conv stride (x box start = dy coord * stride + tap offset)
-  int tap_dy, tap_dx;             // filled per launch? no: derived from blockIdx (see kernel)
-  int kw, pe;
-  int co_tiles, ci_tiles;
-  int co, ci, taps;
-  float* partial;                 // [split][tap][co_pad][ci]  (co_pad = co_tiles*128)
+  int stride, kw, pe;
+  int co_tiles, ci_tiles, taps;
+  int ci;                         // channels of x (row length of the partial buffer)
+  float* partial;                 // [split][tap][co_tiles*128][ci]
 };
 
-template <int BN, int STAGES>
+// CA / CB: channels per TMA chunk of dY / X (64, 32 or 16 -> swizzle 128/64/32 B); BN: input channels per CTA
+template <int CA, int CB, int BN>
+struct WgradCfg {
+  static constexpr int NA = BM / CA, NB = BN / CB;
+  static constexpr uint32_t CHUNK_A = WG_KP * CA * 2, CHUNK_B = WG_KP * CB * 2;     // >= 2 KB, multiples of 1 KB
+  static constexpr uint32_t A_BYTES = NA * CHUNK_A, B_BYTES = NB * CHUNK_B, STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES_RAW = (int)(180224u / STAGE_BYTES);
+  static constexpr int STAGES = STAGES_RAW > 6 ? 6 : (STAGES_RAW < 2 ? 2 : STAGES_RAW);
+  static constexpr uint32_t TMEM_COLS = BN <= 32 ? 32 : (BN <= 64 ? 64 : (BN <= 128 ? 128 : 256));
+  static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + 1024 + 256;
+};
+
+template <int CA, int CB, int BN>
 __global__ void __launch_bounds__(NTHREADS)
 tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ CUtensorMap tmX,
                 const __grid_constant__ WgradParams P) {
-  // A = dY box: two 64-channel chunks (M = 128 output channels), MN-major; B = X box: BN/64 chunks, MN-major
-  constexpr uint32_t CHUNK_BYTES = WG_KP * 128;                 // 64 pixels x 64 channels x 2 B
-  constexpr uint32_t A_BYTES = 2 * CHUNK_BYTES, B_BYTES = (BN / 64) * CHUNK_BYTES, STAGE_BYTES = A_BYTES + B_BYTES;
+  using Cfg = WgradCfg<CA, CB, BN>;
+  constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  uint64_t* full_bar = (uint64_t*)(smem + STAGES * STAGE_BYTES);
+  uint64_t* full_bar = (uint64_t*)(smem + STAGES * Cfg::STAGE_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full = empty_bar + STAGES;
   uint32_t* tmem_slot = (uint32_t*)(tmem_full + 1);
@@ -379,7 +430,7 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant_
     mbar_init(tmem_full, 1);
     fence_mbar_init();
   }
-  if (warp == 2) tmem_alloc(tmem_slot, BN < 32 ? 32 : BN);
+  if (warp == 2) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -395,14 +446,14 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant_
         const int tn = t / P.tiles_y;
         const int x0 = tx * P.tw, y0 = ty * P.th, n0 = tn * P.tn;
         mbar_wait(&empty_bar[stage], phase ^ 1);
-        uint8_t* sa = smem + stage * STAGE_BYTES;
-        mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
+        uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+        mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
 #pragma unroll
-        for (int c = 0; c < 2; ++c)
-          tma_load_4d(sa + c * CHUNK_BYTES, &tmDY, &full_bar[stage], cot * 128 + c * 64, x0, y0, n0);
+        for (int c = 0; c < Cfg::NA; ++c)
+          tma_load_4d(sa + c * Cfg::CHUNK_A, &tmDY, &full_bar[stage], cot * BM + c * CA, x0, y0, n0);
 #pragma unroll
-        for (int c = 0; c < BN / 64; ++c)
-          tma_load_4d(sa + A_BYTES + c * CHUNK_BYTES, &tmX, &full_bar[stage], cit * BN + c * 64,
+        for (int c = 0; c < Cfg::NB; ++c)
+          tma_load_4d(sa + Cfg::A_BYTES + c * Cfg::CHUNK_B, &tmX, &full_bar[stage], cit * BN + c * CB,
                       x0 * P.stride - P.pe + tb, y0 * P.stride - P.pe + ta, n0);
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
@@ -410,18 +461,19 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant_
   } else if (warp == 1) {
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc_bf16(BM, BN, 1, 1);
+      // MN-major: CA (CB) channels per swizzled row; LBO = distance between channel chunks (one TMA box),
+      // SBO = distance between 8-pixel K groups; one UMMA consumes 16 pixels
+      constexpr uint32_t SBO_A = 8 * CA * 2, SBO_B = 8 * CB * 2, KADV_A = (16 * CA * 2) >> 4, KADV_B = (16 * CB * 2) >> 4;
       int stage = 0; uint32_t phase = 0;
       for (int ks = 0; ks < ksteps; ++ks) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
-        const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
-        // MN-major SW128: 64 MN elements per 128-byte row; LBO = distance between 64-element MN chunks
-        // (= one TMA box), SBO = distance between 8-row K groups (1024 B); UMMA_K = 16 rows = 2048 B
-        const uint64_t adesc = make_smem_desc(sa, CHUNK_BYTES, 1024, LAYOUT_SW128);
-        const uint64_t bdesc = make_smem_desc(sa + A_BYTES, CHUNK_BYTES, 1024, LAYOUT_SW128);
+        const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+        const uint64_t adesc = make_smem_desc(sa, Cfg::CHUNK_A, SBO_A, layout_for(CA));
+        const uint64_t bdesc = make_smem_desc(sa + Cfg::A_BYTES, Cfg::CHUNK_B, SBO_B, layout_for(CB));
 #pragma unroll
         for (int k = 0; k < WG_KP / 16; ++k)
-          umma_bf16(tmem_base, adesc + (uint64_t)(k * (2048 >> 4)), bdesc + (uint64_t)(k * (2048 >> 4)), idesc,
+          umma_bf16(tmem_base, adesc + (uint64_t)(k * KADV_A), bdesc + (uint64_t)(k * KADV_B), idesc,
                     (ks > 0 || k > 0) ? 1u : 0u);
         umma_commit(&empty_bar[stage]);
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -431,14 +483,13 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant_
   } else {
     const int q = warp & 3;
     const int row = q * 32 + lane;            // output channel within the 128-tile
-    const int co = cot * 128 + row;
-    float* out = P.partial + ((((long long)split * P.taps + tap) * (P.co_tiles * 128) + co) * (long long)P.ci) + cit * BN;
+    float* out = P.partial + ((((long long)split * P.taps + tap) * (P.co_tiles * BM) + cot * BM + row) * (long long)P.ci) + cit * BN;
     if (ksteps > 0) {
       mbar_wait(tmem_full, 0);
       tc_fence_after();
     }
 #pragma unroll 1
-    for (int cc = 0; cc < BN; cc += 32) {
+    for (int cc = 0; cc < (int)Cfg::TMEM_COLS; cc += 32) {
       float v[32];
       if (ksteps > 0) {
         tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)cc, v);
@@ -448,56 +499,55 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant_
       }
 #pragma unroll
       for (int j = 0; j < 32; j += 4)
-        *reinterpret_cast<float4*>(out + cc + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        if (cc + j < BN) *reinterpret_cast<float4*>(out + cc + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
     }
     tc_fence_before();
   }
   __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, BN < 32 ? 32 : BN);
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
   }
 }
 
-// dw[co][ci][tap] = sum_split partial[split][tap][co][ci]
+// dw[co][ci][tap] = sum_split partial[split][tap][co][ci]   (co < co_real, ci < ci_real)
 __global__ void wgrad_finalize_kernel(const float* __restrict__ partial, float* __restrict__ dw, int splits, int taps,
-                                      int co, int co_pad, int ci) {
-  const int64_t total = (int64_t)co * ci * taps;
+                                      int co_real, int co_pad, int ci_real, int ci_pad) {
+  const int64_t total = (int64_t)co_real * ci_real * taps;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    // iterate with ci fastest for coalesced partial reads
-    int c_i = (int)(i % ci);
-    int64_t r = i / ci;
+    int c_i = (int)(i % ci_real);          // ci fastest: coalesced partial reads
+    int64_t r = i / ci_real;
     int tap = (int)(r % taps);
     int c_o = (int)(r / taps);
     float acc = 0.f;
     for (int s = 0; s < splits; ++s)
-      acc += __ldg(partial + (((int64_t)s * taps + tap) * co_pad + c_o) * ci + c_i);
-    dw[((int64_t)c_o * ci + c_i) * taps + tap] = acc;
+      acc += __ldg(partial + (((int64_t)s * taps + tap) * co_pad + c_o) * ci_pad + c_i);
+    dw[((int64_t)c_o * ci_real + c_i) * taps + tap] = acc;
   }
 }
 
 struct WgradPlan {
-  int BN, tw, th, tn, tiles_x, tiles_y, tiles_n, splits, tiles_per_split, co_tiles, ci_tiles, taps;
+  int CA, CB, BN, tw, th, tn, tiles_x, tiles_y, tiles_n, splits, tiles_per_split, co_tiles, ci_tiles, taps;
   int64_t ws_bytes;
 };
 
-static void pick_pixel_tile(int dw, int dh, int& tw, int& th, int& tn) {
-  tw = 1;
-  while (tw < dw && tw < WG_KP) tw <<= 1;
-  th = 1;
-  while (th < dh && tw * th < WG_KP) th <<= 1;
-  tn = WG_KP / (tw * th);
+static bool wgrad_bn(int c, int& cb, int& bn) {
+  cb = chunk_for(c);
+  if (cb == 64) { bn = (c % 256 == 0) ? 256 : ((c % 128 == 0) ? 128 : 64); return true; }
+  if (cb == 32) { bn = c; return c == 32 || c == 96; }
+  bn = c;
+  return c == 16;
 }
 
-static WgradPlan plan_wgrad(const nemar_tensor* x, const nemar_tensor* dy, int kh, int kw) {
-  WgradPlan p;
-  p.BN = (x->c % 256 == 0) ? 256 : ((x->c % 128 == 0) ? 128 : 64);
-  pick_pixel_tile(dy->w, dy->h, p.tw, p.th, p.tn);
+static bool plan_wgrad(const nemar_tensor* x, const nemar_tensor* dy, int kh, int kw, WgradPlan& p) {
+  if (!wgrad_bn(x->c, p.CB, p.BN)) return false;
+  p.CA = chunk_for(dy->c);
+  pick_tile(dy->w, dy->h, p.tw, p.th, p.tn, WG_KP);
   p.tiles_x = (dy->w + p.tw - 1) / p.tw;
   p.tiles_y = (dy->h + p.th - 1) / p.th;
   p.tiles_n = (dy->n + p.tn - 1) / p.tn;
   p.taps = kh * kw;
-  p.co_tiles = (dy->c + 127) / 128;
+  p.co_tiles = (dy->c + BM - 1) / BM;
   p.ci_tiles = x->c / p.BN;
   const int total = p.tiles_x * p.tiles_y * p.tiles_n;
   const int base = p.taps * p.co_tiles * p.ci_tiles;
@@ -506,68 +556,87 @@ static WgradPlan plan_wgrad(const nemar_tensor* x, const nemar_tensor* dy, int k
   if (splits < 1) splits = 1;
   p.tiles_per_split = (total + splits - 1) / splits;
   p.splits = (total + p.tiles_per_split - 1) / p.tiles_per_split;
-  p.ws_bytes = (int64_t)p.splits * p.taps * p.co_tiles * 128 * x->c * 4;
-  return p;
+  p.ws_bytes = (int64_t)p.splits * p.taps * p.co_tiles * BM * x->c * 4;
+  return true;
 }
 
-template <int BN>
-static int launch_wgrad(const CUtensorMap& tmDY, const CUtensorMap& tmX, const WgradParams& P, const WgradPlan& pl, cudaStream_t s) {
-  constexpr int STAGES = (BN == 256) ? 4 : ((BN == 128) ? 4 : 6);
-  constexpr uint32_t CHUNK = WG_KP * 128;
-  size_t smem = (size_t)STAGES * (2 * CHUNK + (BN / 64) * CHUNK) + 1024 + 256;
+template <int CA, int CB, int BN>
+static int launch_wgrad_t(const CUtensorMap& tmDY, const CUtensorMap& tmX, const WgradParams& P, const WgradPlan& pl, cudaStream_t s) {
+  using Cfg = WgradCfg<CA, CB, BN>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(tc_wgrad_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(tc_wgrad_kernel<CA, CB, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
     NEMAR_REQUIRE(e == cudaSuccess, "cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
     attr_set = true;
   }
   dim3 grid((unsigned)(pl.taps * pl.co_tiles * pl.ci_tiles), (unsigned)pl.splits);
-  tc_wgrad_kernel<BN, STAGES><<<grid, NTHREADS, smem, s>>>(tmDY, tmX, P);
+  tc_wgrad_kernel<CA, CB, BN><<<grid, NTHREADS, Cfg::SMEM, s>>>(tmDY, tmX, P);
   NEMAR_LAUNCH_CHECK();
   return 0;
+}
+
+template <int CA>
+static int launch_wgrad_a(const CUtensorMap& d, const CUtensorMap& x, const WgradParams& P, const WgradPlan& pl, cudaStream_t s) {
+  if (pl.CB == 64) {
+    if (pl.BN == 256) return launch_wgrad_t<CA, 64, 256>(d, x, P, pl, s);
+    if (pl.BN == 128) return launch_wgrad_t<CA, 64, 128>(d, x, P, pl, s);
+    return launch_wgrad_t<CA, 64, 64>(d, x, P, pl, s);
+  }
+  if (pl.CB == 32) {
+    if (pl.BN == 96) return launch_wgrad_t<CA, 32, 96>(d, x, P, pl, s);
+    return launch_wgrad_t<CA, 32, 32>(d, x, P, pl, s);
+  }
+  return launch_wgrad_t<CA, 16, 16>(d, x, P, pl, s);
 }
 
 }  // namespace
 
 bool tc_wgrad_supported(const nemar_tensor* x, const nemar_tensor* dy, int kh, int kw, int stride, int pe) {
-  if (!tc_view_ok(x) || !tc_view_ok(dy) || dy->pad != 0) return false;
+  if (!tc_view_ok(x, false) || !tc_view_ok(dy, false) || dy->pad != 0) return false;
   if (kh * kw > MAX_TAPS || !(stride == 1 || stride == 2) || pe < 0) return false;
+  WgradPlan p;
+  nemar_tensor xx = *x;
+  xx.h += 2 * x->pad; xx.w += 2 * x->pad; xx.pad = 0;
+  if (!plan_wgrad(&xx, dy, kh, kw, p)) return false;
   return get_encode() != nullptr;
 }
 
 int64_t tc_wgrad_workspace(const nemar_tensor* x, const nemar_tensor* dy, int kh, int kw, int stride, int pe) {
   if (!tc_wgrad_supported(x, dy, kh, kw, stride, pe)) return 0;
-  return plan_wgrad(x, dy, kh, kw).ws_bytes;
+  WgradPlan p;
+  plan_wgrad(x, dy, kh, kw, p);
+  return p.ws_bytes;
 }
 
-int tc_wgrad(const nemar_tensor* x_in, const nemar_tensor* dy, float* dw, int kh, int kw, int stride, int pe,
-             void* workspace, int64_t workspace_bytes, cudaStream_t s) {
+int tc_wgrad(const nemar_tensor* x_in, const nemar_tensor* dy, float* dw, int co_real, int ci_real, int kh, int kw,
+             int stride, int pe, void* workspace, int64_t workspace_bytes, cudaStream_t s) {
   NEMAR_REQUIRE(tc_wgrad_supported(x_in, dy, kh, kw, stride, pe), "tc_wgrad: unsupported geometry");
   nemar_tensor x = *x_in;
   x.h += 2 * x.pad; x.w += 2 * x.pad; x.pad = 0;      // halo = real data; `pe` is relative to the padded buffer
-  WgradPlan pl = plan_wgrad(&x, dy, kh, kw);
+  WgradPlan pl;
+  plan_wgrad(&x, dy, kh, kw, pl);
   NEMAR_REQUIRE(workspace && workspace_bytes >= pl.ws_bytes, "tc_wgrad: workspace too small (%lld < %lld)",
                 (long long)workspace_bytes, (long long)pl.ws_bytes);
   CUtensorMap tmDY, tmX;
-  int rc = make_act_map(&tmDY, dy, 64, pl.tw, pl.th, pl.tn, 1);
+  int rc = make_act_map(&tmDY, dy, pl.CA, pl.tw, pl.th, pl.tn, 1);
   if (rc) return rc;
-  rc = make_act_map(&tmX, &x, 64, pl.tw, pl.th, pl.tn, stride);
+  rc = make_act_map(&tmX, &x, pl.CB, pl.tw, pl.th, pl.tn, stride);
   if (rc) return rc;
   WgradParams P;
   P.tw = pl.tw; P.th = pl.th; P.tn = pl.tn;
   P.tiles_x = pl.tiles_x; P.tiles_y = pl.tiles_y; P.tiles_n = pl.tiles_n;
   P.tiles_per_split = pl.tiles_per_split;
-  P.stride = stride; P.kw = kw; P.pe = pe; P.tap_dy = 0; P.tap_dx = 0;
-  P.co_tiles = pl.co_tiles; P.ci_tiles = pl.ci_tiles;
-  P.co = dy->c; P.ci = x.c; P.taps = pl.taps;
+  P.stride = stride; P.kw = kw; P.pe = pe;
+  P.co_tiles = pl.co_tiles; P.ci_tiles = pl.ci_tiles; P.taps = pl.taps;
+  P.ci = x.c;
   P.partial = (float*)workspace;
-  if (pl.BN == 256) rc = launch_wgrad<256>(tmDY, tmX, P, pl, s);
-  else if (pl.BN == 128) rc = launch_wgrad<128>(tmDY, tmX, P, pl, s);
-  else rc = launch_wgrad<64>(tmDY, tmX, P, pl, s);
+  if (pl.CA == 64) rc = launch_wgrad_a<64>(tmDY, tmX, P, pl, s);
+  else if (pl.CA == 32) rc = launch_wgrad_a<32>(tmDY, tmX, P, pl, s);
+  else rc = launch_wgrad_a<16>(tmDY, tmX, P, pl, s);
   if (rc) return rc;
-  const int64_t total = (int64_t)dy->c * x.c * pl.taps;
-  wgrad_finalize_kernel<<<grid_for(total, 256), 256, 0, s>>>((const float*)workspace, dw, pl.splits, pl.taps, dy->c,
-                                                              pl.co_tiles * 128, x.c);
+  const int64_t total = (int64_t)co_real * ci_real * pl.taps;
+  wgrad_finalize_kernel<<<grid_for(total, 256), 256, 0, s>>>((const float*)workspace, dw, pl.splits, pl.taps, co_real,
+                                                              pl.co_tiles * BM, ci_real, x.c);
   NEMAR_LAUNCH_CHECK();
   return 0;
 }

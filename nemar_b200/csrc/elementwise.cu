@@ -180,6 +180,28 @@ NEMAR_API int nemar_copy_view(const nemar_tensor* src, const nemar_tensor* dst, 
   return 0;
 }
 
+__global__ void cast_view_kernel(TView s, TView d) {
+  const int64_t total = (int64_t)d.n * d.h * d.w * d.c;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    int ch = (int)(i % d.c);
+    int64_t r = i / d.c;
+    int x = (int)(r % d.w); r /= d.w;
+    int y = (int)(r % d.h);
+    int nn = (int)(r / d.h);
+    st_rt(d.ptr, d.dtype, d.pix(nn, y, x) + ch, ld_rt(s.ptr, s.dtype, s.pix(nn, y, x) + ch));
+  }
+}
+
+NEMAR_API int nemar_cast_view(const nemar_tensor* src, const nemar_tensor* dst, void* stream) {
+  NEMAR_REQUIRE(view_ok(src) && view_ok(dst) && same_shape(src, dst), "cast_view: bad args");
+  TView s = make_view(src), d = make_view(dst);
+  int64_t total = (int64_t)d.n * d.h * d.w * d.c;
+  cast_view_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(s, d);
+  NEMAR_LAUNCH_CHECK();
+  return 0;
+}
+
 template <typename T, int V>
 __global__ void copy_view_bwd_kernel(TView ds, TView dd, int pad_mode, int accumulate) {
   // ds: gradient wrt the copy source (written), dd: gradient wrt the (padded) destination (read+fold)

@@ -123,14 +123,17 @@ class Concat(Function):
 # convolution
 # ------------------------------------------------------------------------------------------------
 class ConvCfg:
-    """Static description of one conv layer call (geometry + epilogue + engine choice)."""
+    """Static description of one conv layer call (geometry + epilogue + engine choice).  cin/cout are the REAL
+    channel counts (the reference's weight shape); cout_p >= cout is the channel count of the output tensor
+    (zero-padded to a multiple of 16 on the tensor-core engine); the input tensor brings its own padding."""
 
     def __init__(self, cin, cout, k, stride=1, pad=0, transposed=False, x_pad=0, act=L.ACT_NONE, stats=False,
-                 out_f32=False, out_pad_t=0, use_tc=False):
+                 out_f32=False, out_pad_t=0, use_tc=False, cout_p=None):
         self.geom = L.ConvGeom(cin, cout, k, k, stride, pad, int(transposed))
         self.cin, self.cout, self.k, self.stride, self.pad = cin, cout, k, stride, pad
         self.transposed, self.x_pad, self.act, self.stats = transposed, x_pad, act, stats
         self.out_f32, self.out_pad_t, self.use_tc = out_f32, out_pad_t, use_tc
+        self.cout_p = cout if cout_p is None else cout_p
 
     def out_hw(self, h, w):
         if not self.transposed:
@@ -141,40 +144,55 @@ class ConvCfg:
 
 
 class PackedWeights:
-    """Per-parameter cache of the forward / backward packs (rebuilt when the weights epoch changes)."""
+    """Per-parameter cache of the forward / backward packs and the padded bias (rebuilt when the weights epoch
+    changes or the layer is called with another channel padding)."""
 
     def __init__(self):
-        self.key = None
-        self.wf = self.wd = None
+        self.cache = {}
 
-    def get(self, weight, cfg, dtype):
-        key = (weights_epoch(), weight.data_ptr(), dtype)
-        if self.key != key:
-            g = cfg.geom
+    def get(self, weight, bias, cfg, dtype, cin_p):
+        key = (dtype, cin_p, cfg.cout_p)
+        ent = self.cache.get(key)
+        stamp = (weights_epoch(), weight.data_ptr())
+        if ent is None or ent[0] != stamp:
             k2 = cfg.k * cfg.k
-            self.wf = torch.empty(cfg.cout * k2 * cfg.cin, dtype=dtype, device=weight.device)
-            self.wd = torch.empty(cfg.cin * k2 * cfg.cout, dtype=dtype, device=weight.device)
-            call("nemar_pack_weights", fptr(weight.detach()), g, L.dtype_code(self.wf), cfg.cin, cfg.cout,
-                 vptr(self.wf), vptr(self.wd), stream())
-            self.key = key
-        return self.wf, self.wd
+            wf = torch.empty(cfg.cout_p * k2 * cin_p, dtype=dtype, device=weight.device)
+            wd = torch.empty(cin_p * k2 * cfg.cout_p, dtype=dtype, device=weight.device)
+            call("nemar_pack_weights", fptr(weight.detach()), cfg.geom, L.dtype_code(wf), cin_p, cfg.cout_p, vptr(wf),
+                 vptr(wd), stream())
+            bp = None
+            if bias is not None:
+                if cfg.cout_p == cfg.cout:
+                    bp = bias.detach()
+                else:
+                    bp = torch.zeros(cfg.cout_p, dtype=torch.float32, device=weight.device)
+                    bp[:cfg.cout].copy_(bias.detach())
+            ent = (stamp, wf, wd, bp)
+            self.cache[key] = ent
+        return ent[1], ent[2], ent[3]
+
+
+def _cast(t, dtype):
+    out = torch.empty(t.shape, dtype=dtype, device=t.device)
+    call("nemar_cast_view", view(t), view(out), stream())
+    return out
 
 
 class Conv2dFn(Function):
     @staticmethod
     def forward(ctx, x, weight, bias, cfg, packed):
         x = _c(x)
-        n, hp, wp, cin = x.shape
+        n, hp, wp, cin_p = x.shape
         h, w = hp - 2 * cfg.x_pad, wp - 2 * cfg.x_pad
         ho, wo = cfg.out_hw(h, w)
-        wf, wd = packed.get(weight, cfg, x.dtype)
+        wf, wd, bp = packed.get(weight, bias, cfg, x.dtype, cin_p)
         ydt = torch.float32 if cfg.out_f32 else x.dtype
-        y = torch.empty((n, ho, wo, cfg.cout), dtype=ydt, device=x.device)
+        y = torch.empty((n, ho, wo, cfg.cout_p), dtype=ydt, device=x.device)
         stats = None
         if cfg.stats:
-            stats = torch.zeros((n, cfg.cout, 2), dtype=torch.float32, device=x.device)
-        call("nemar_conv2d_fprop", view(x, cfg.x_pad), vptr(wf), cfg.cin, fptr(bias.detach()) if bias is not None else None,
-             cfg.geom, cfg.act, view(y), fptr(stats), int(cfg.use_tc), stream())
+            stats = torch.zeros((n, cfg.cout_p, 2), dtype=torch.float32, device=x.device)
+        call("nemar_conv2d_fprop", view(x, cfg.x_pad), vptr(wf), cin_p, fptr(bp), cfg.geom, cfg.act, view(y), fptr(stats),
+             int(cfg.use_tc), stream())
         ctx.cfg, ctx.wd = cfg, wd
         ctx.has_bias = bias is not None
         ctx.save_for_backward(x, weight, y if cfg.act != L.ACT_NONE else None)
@@ -193,21 +211,24 @@ class Conv2dFn(Function):
             call("nemar_act_bwd", view(y), view(dy), cfg.act, view(g), stream())
         else:
             g = dy
+        # the tensor-core engine wants the output gradient in the storage dtype of the layer
+        gk = _cast(g, x.dtype) if (cfg.use_tc and g.dtype != x.dtype) else g
         dx = dw = db = None
         if ctx.needs_input_grad[0]:
             dx = torch.empty_like(x)
-            call("nemar_conv2d_dgrad", view(g), vptr(ctx.wd), cfg.cout, cfg.geom, view(dx, cfg.x_pad),
-                 int(cfg.use_tc), stream())
+            call("nemar_conv2d_dgrad", view(gk), vptr(ctx.wd), cfg.cout_p, cfg.geom, view(dx, cfg.x_pad), int(cfg.use_tc),
+                 stream())
         if ctx.needs_input_grad[1]:
-            dw = torch.empty_like(weight)
-            xv, gv = view(x, cfg.x_pad), view(g)
+            dw = torch.empty(weight.shape, dtype=torch.float32, device=x.device)
+            xv, gv = view(x, cfg.x_pad), view(gk)
             ws_bytes = L.lib().nemar_conv2d_wgrad_workspace(L.C.byref(xv), L.C.byref(gv), L.C.byref(cfg.geom),
                                                             int(cfg.use_tc))
             ws = torch.empty(max(int(ws_bytes), 16), dtype=torch.uint8, device=x.device) if ws_bytes > 0 else None
             call("nemar_conv2d_wgrad", xv, gv, cfg.geom, fptr(dw), vptr(ws), i64(ws_bytes), int(cfg.use_tc), stream())
         if ctx.has_bias and ctx.needs_input_grad[2]:
-            db = torch.empty(cfg.cout, dtype=torch.float32, device=x.device)
+            db = torch.empty(cfg.cout_p, dtype=torch.float32, device=x.device)
             call("nemar_bias_grad", view(g), fptr(db), stream())
+            db = db[:cfg.cout]
         return dx, dw, db, None, None
 
 
@@ -358,16 +379,24 @@ class FlowGridFn(Function):
     @staticmethod
     def forward(ctx, off, xs, ys):
         off = _c(off)
-        n, h, w, two = off.shape
-        assert two == 2 and off.dtype == torch.float32
+        n, h, w, cs = off.shape          # cs >= 2: the conv head may pad its output channels (zeros)
+        assert cs >= 2 and off.dtype == torch.float32
         grid = torch.empty((n, h, w, 2), dtype=torch.float32, device=off.device)
-        call("nemar_flow_grid_fwd", fptr(off), i64(h * w * 2), i64(1), i64(w * 2), i64(2), fptr(xs), fptr(ys), n, h, w,
+        call("nemar_flow_grid_fwd", fptr(off), i64(h * w * cs), i64(1), i64(w * cs), i64(cs), fptr(xs), fptr(ys), n, h, w,
              fptr(grid), stream())
+        ctx.cs = cs
         return grid
 
     @staticmethod
     def backward(ctx, dgrid):
-        return dgrid, None, None
+        if ctx.cs == 2:
+            return dgrid, None, None
+        dgrid = _c(dgrid)
+        n, h, w, _ = dgrid.shape
+        doff = torch.empty((n, h, w, ctx.cs), dtype=torch.float32, device=dgrid.device)
+        call("nemar_fill_channels", view(doff), 2, ctx.cs - 2, stream())
+        call("nemar_copy_view", view(dgrid), view(doff, 0, 0, 2), L.PAD_ZERO, stream())
+        return doff, None, None
 
 
 class GridSampleFn(Function):
@@ -426,13 +455,13 @@ class SmoothnessFn(Function):
     @staticmethod
     def forward(ctx, off, img, alpha, scale):
         off = _c(off)
-        n, h, w, _ = off.shape
+        n, h, w, cs = off.shape
         loss = torch.zeros(1, dtype=torch.float32, device=off.device)
         use_img = img is not None and alpha > 0.0
         if use_img:
             img = _c(img)
             assert img.shape[0] == n and img.shape[2] == h and img.shape[3] == w
-        call("nemar_smoothness_fwd", fptr(off), i64(h * w * 2), i64(1), i64(w * 2), i64(2),
+        call("nemar_smoothness_fwd", fptr(off), i64(h * w * cs), i64(1), i64(w * cs), i64(cs),
              fptr(img) if use_img else None, int(img.shape[1]) if use_img else 0, float(alpha), n, h, w, float(scale),
              fptr(loss), stream())
         ctx.save_for_backward(off, img if use_img else None)
@@ -443,10 +472,10 @@ class SmoothnessFn(Function):
     def backward(ctx, g):
         off, img = ctx.saved_tensors
         alpha, scale = ctx.meta
-        n, h, w, _ = off.shape
+        n, h, w, cs = off.shape
         g = _c(g.reshape(1).to(torch.float32))
         doff = torch.zeros_like(off)
-        call("nemar_smoothness_bwd", fptr(off), i64(h * w * 2), i64(1), i64(w * 2), i64(2), fptr(img),
+        call("nemar_smoothness_bwd", fptr(off), i64(h * w * cs), i64(1), i64(w * cs), i64(cs), fptr(img),
              int(img.shape[1]) if img is not None else 0, float(alpha), n, h, w, float(scale), fptr(g), fptr(doff),
              stream())
         return doff, None, None, None
@@ -497,22 +526,25 @@ class MSEConstFn(Function):
     """scale * mean((pred - target)^2) over an engine tensor (LSGAN, networks.py:237-238,273-275)."""
 
     @staticmethod
-    def forward(ctx, pred, target, scale):
+    def forward(ctx, pred, target, scale, c=None):
         pred = _c(pred)
+        c = pred.shape[3] if c is None else c       # real channels (the head may pad its output with zeros)
         out = torch.zeros(1, dtype=torch.float32, device=pred.device)
-        call("nemar_mse_const_fwd", view(pred), float(target), float(scale), fptr(out), stream())
+        call("nemar_mse_const_fwd", view(pred, 0, 0, c), float(target), float(scale), fptr(out), stream())
         ctx.save_for_backward(pred)
-        ctx.meta = (target, scale)
+        ctx.meta = (target, scale, c)
         return out
 
     @staticmethod
     def backward(ctx, g):
         (pred,) = ctx.saved_tensors
-        target, scale = ctx.meta
+        target, scale, c = ctx.meta
         g = _c(g.reshape(1).to(torch.float32))
         dp = torch.empty_like(pred)
-        call("nemar_mse_const_bwd", view(pred), float(target), float(scale), fptr(g), view(dp), stream())
-        return dp, None, None
+        if pred.shape[3] > c:
+            call("nemar_fill_channels", view(dp), c, pred.shape[3] - c, stream())
+        call("nemar_mse_const_bwd", view(pred, 0, 0, c), float(target), float(scale), fptr(g), view(dp, 0, 0, c), stream())
+        return dp, None, None, None
 
 
 class LinearFn(Function):

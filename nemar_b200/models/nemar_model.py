@@ -119,7 +119,7 @@ class NEMARModel(BaseModel):
         for i, netD in enumerate(self._scales()):
             b = img_B.detach() if detach else img_B
             pred = netD.forward_engine(pyr_A[i], self._resized(b, i))
-            term = self.criterionGAN(pred, target_is_real)
+            term = self.criterionGAN.engine(pred, target_is_real)
             total = term if total is None else total + term
         return total
 

@@ -22,12 +22,20 @@ class Holder(nn.Module):
         raise RuntimeError("container module")
 
 
-def tc_policy(cin, cout, k, stride, transposed, dtype):
-    """Should this layer run on the tcgen05 engine?"""
-    if CONFIG.conv_engine != "auto" or dtype != torch.bfloat16:
+def tc_policy(cin, cout, k, stride, transposed, dtype, cin_p):
+    """Should this layer run on the tcgen05 engine?  (bf16 storage, input channels already a multiple of 16)"""
+    if CONFIG.conv_engine != "auto" or dtype != torch.bfloat16 or cin_p % 16 != 0:
         return False
     geom = L.ConvGeom(cin, cout, k, k, stride, 0, int(transposed))
     return bool(L.lib().nemar_conv2d_tc_supported(L.C.byref(geom), L.BF16, 0, 0))
+
+
+def image_channels(nc):
+    """Channel count of the engine tensor holding `nc` image channels: padded to 16 (zeros) when the tensor-core
+    engine is active so that 3/6-channel images fit a tcgen05 K chunk."""
+    if CONFIG.conv_engine == "auto" and CONFIG.dtype == torch.bfloat16:
+        return (nc + 15) // 16 * 16
+    return nc
 
 
 class Conv(nn.Module):
@@ -49,11 +57,12 @@ class Conv(nn.Module):
 
     def run(self, x, x_pad=0, act=L.ACT_NONE, stats=False, out_f32=False):
         cin, cout, k, stride, pad, transposed, opt = self.meta
-        key = (x_pad, act, stats, out_f32, x.dtype, CONFIG.conv_engine)
+        key = (x_pad, act, stats, out_f32, x.dtype, CONFIG.conv_engine, x.shape[3])
         cfg = self._cfgs.get(key)
         if cfg is None:
-            use_tc = (not out_f32) and tc_policy(cin, cout, k, stride, transposed, x.dtype)
-            cfg = F.ConvCfg(cin, cout, k, stride, pad, transposed, x_pad, act, stats, out_f32, opt, use_tc)
+            use_tc = tc_policy(cin, cout, k, stride, transposed, x.dtype, x.shape[3])
+            cout_p = (cout + 15) // 16 * 16 if use_tc else cout
+            cfg = F.ConvCfg(cin, cout, k, stride, pad, transposed, x_pad, act, stats, out_f32, opt, use_tc, cout_p)
             self._cfgs[key] = cfg
         return F.Conv2dFn.apply(x, self.weight, self.bias, cfg, self._packed)
 
@@ -124,7 +133,7 @@ class ResnetGenerator(nn.Module):
     def forward(self, x):
         m, nb = self.model, self.n_blocks
         g = lambda i: getattr(m, str(i))
-        t = F.ImagesToNHWC.apply(3, L.PAD_REFLECT, CONFIG.dtype, self.input_nc, x)
+        t = F.ImagesToNHWC.apply(3, L.PAD_REFLECT, CONFIG.dtype, image_channels(self.input_nc), x)
         t = conv_in_act(g(1), t, 3, L.ACT_RELU)
         t = conv_in_act(g(4), t, 0, L.ACT_RELU)
         t = conv_in_act(g(7), t, 0, L.ACT_RELU, out_pad=1 if nb > 0 else 0)
@@ -162,11 +171,11 @@ class NLayerDiscriminator(nn.Module):
 
     def forward_engine(self, *imgs):
         m = self.model
-        t = F.ImagesToNHWC.apply(0, L.PAD_ZERO, CONFIG.dtype, self.input_nc, *imgs)
+        t = F.ImagesToNHWC.apply(0, L.PAD_ZERO, CONFIG.dtype, image_channels(self.input_nc), *imgs)
         t = getattr(m, "0").run(t, act=L.ACT_LRELU)
         for idx in self.mid:
             t = conv_in_act(getattr(m, str(idx)), t, 0, L.ACT_LRELU)
-        return getattr(m, str(self.last)).run(t, out_f32=True)   # [N,h,w,1] fp32
+        return getattr(m, str(self.last)).run(t, out_f32=True)   # [N,h,w,>=1] fp32 (channel 0 is the prediction)
 
     def forward(self, x):
         return F.ToNCHW.apply(self.forward_engine(x), 1)
@@ -188,6 +197,13 @@ class GANLoss(nn.Module):
         self.register_buffer("fake_label", torch.tensor(target_fake_label))
         self.gan_mode = gan_mode
         self.real_value, self.fake_value = float(target_real_label), float(target_fake_label)
+
+    def engine(self, prediction, target_is_real):
+        """LSGAN term on the discriminator's engine-layout output [N,h,w,C>=1] (channel 0 real, rest padding)."""
+        target = self.real_value if target_is_real else self.fake_value
+        if self.gan_mode == "lsgan":
+            return F.MSEConstFn.apply(prediction, target, 1.0, 1).squeeze(0)
+        return self.__call__(F.ToNCHW.apply(prediction, 1), target_is_real)
 
     def __call__(self, prediction, target_is_real):
         target = self.real_value if target_is_real else self.fake_value

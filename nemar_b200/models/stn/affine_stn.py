@@ -41,7 +41,7 @@ class AffineNetwork(nn.Module):
         last.bias.data.zero_()
 
     def forward(self, img_a, img_b):
-        x = F.ImagesToNHWC.apply(0, L.PAD_ZERO, CONFIG.dtype, self.in_nc, img_a, img_b)
+        x = F.ImagesToNHWC.apply(0, L.PAD_ZERO, CONFIG.dtype, N.image_channels(self.in_nc), img_a, img_b)
         for i in range(self.nconvs):
             x = getattr(self.convs, str(i)).run(x)
         feat = F.ToNCHW.apply(x, self.feat_c)             # (c,h,w) flatten order of the reference

@@ -56,7 +56,7 @@ class ResUnet(nn.Module):
 
     def forward(self, img_a, img_b):
         """-> offsets as an engine tensor [N,H,W,2] fp32 (channels-last == the sampling-grid layout)."""
-        x = F.ImagesToNHWC.apply(0, L.PAD_ZERO, CONFIG.dtype, self.in_nc, img_a, img_b)
+        x = F.ImagesToNHWC.apply(0, L.PAD_ZERO, CONFIG.dtype, N.image_channels(self.in_nc), img_a, img_b)
         skips = {}
         for i in range(1, self.ndown_blocks + 1):
             x, skips[i] = getattr(self, "down_%d" % i).run(x)
