@@ -189,10 +189,34 @@ def run_engine(args):
     print(json.dumps(out))
 
 
+def pick_cpu_threads():
+    """Host threads for the CPU arm: all the cores this process may use, unless fewer threads are faster (cgroup
+    quotas / SMT oversubscription make MKL-DNN collapse at 128 threads on the GPU boxes) — short calibration."""
+    try:
+        avail = len(os.sched_getaffinity(0))
+    except AttributeError:
+        avail = os.cpu_count() or 1
+    x = torch.randn(2, 64, 128, 128)
+    w = torch.randn(64, 64, 3, 3)
+    best, best_t = 1, float("inf")
+    cands = sorted({c for c in (8, 16, 32, 64, avail) if c <= avail} | {min(avail, 8)})
+    for c in cands:
+        torch.set_num_threads(c)
+        torch.nn.functional.conv2d(x, w, padding=1)
+        t0 = time.time()
+        for _ in range(3):
+            torch.nn.functional.conv2d(x, w, padding=1)
+        dt = time.time() - t0
+        if dt < best_t:
+            best, best_t = c, dt
+    torch.set_num_threads(best)
+    return best
+
+
 def cpu_baseline(size, budget_s, batch=2, stn_type="unet", n_blocks=9):
     """The oracle port of the reference's CPU path, timed on this box's host cores on a bounded sample."""
     from oracle import nemar_oracle as O
-    torch.set_num_threads(os.cpu_count() or 1)
+    pick_cpu_threads()
     cfg = O.OracleConfig(stn_type=stn_type, n_blocks=n_blocks, height=size, width=size)
     T, R, Ds = O.make_states(cfg, seed=0, live_head=False)
     A, B = O.synthetic_batch(batch, size, size, seed=1)
@@ -214,7 +238,7 @@ def run_reference(args):
     if int(os.environ.get("RANK", "0")) != 0:
         return
     from oracle import nemar_oracle as O
-    torch.set_num_threads(os.cpu_count() or 1)
+    pick_cpu_threads()
     batch = 2
     cfg = O.OracleConfig(stn_type="unet", n_blocks=9, height=args.size, width=args.size)
     T, R, Ds = O.make_states(cfg, seed=0, live_head=False)

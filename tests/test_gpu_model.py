@@ -97,36 +97,50 @@ def test_checkpoint_roundtrip_reference_keys(tmp_path):
     model.load_networks("latest")
 
 
-def _oracle_grads(cfg, T, R, Ds, A, B, dtype):
+def _oracle_grads(cfg, T, R, Ds, A, B, dtype, autocast=False):
     def go():
         Tc, Rc, Dc = O.cast_states(dtype, T, R, Ds)
         st = O.OracleStep(cfg, Tc, Rc, Dc)
-        st.step(A.to(dtype), B.to(dtype))
+        if autocast:
+            with torch.autocast("cpu", dtype=torch.bfloat16):
+                st.step(A.to(dtype), B.to(dtype))
+        else:
+            st.step(A.to(dtype), B.to(dtype))
         return {k: [g.double() for g in v] for k, v in st.grads.items()}
     return O.run_in_dtype(dtype, go)
 
 
-@pytest.mark.parametrize("name,precision,factor,floor", [("c1_affine64", "fp32", 4.0, 1e-3), ("c4_multires256", "fp32", 4.0, 1e-3),
-                                                         ("c1_affine64", "bf16", 0.0, 0.35)])
-def test_gradients_vs_fp64_oracle(name, precision, factor, floor):
+@pytest.mark.parametrize("name,precision,engine", [("c1_affine64", "fp32", "generic"), ("c4_multires256", "fp32", "generic"),
+                                                   ("c1_affine64", "bf16", "generic"), ("c1_affine64", "bf16", "auto"),
+                                                   ("c4_multires256", "bf16", "auto")])
+def test_gradients_vs_fp64_oracle(name, precision, engine):
     """Per-tensor weight gradients of both optimizer phases after one optimize_parameters.  Truth = the oracle in
-    fp64.  fp32 engine: error <= 4x the error the reference's own fp32 arithmetic (oracle fp32) makes, floor 1e-3.
-    bf16 engine: norm-wise error <= 35 % per tensor (bf16 has 8 mantissa bits and the LSGAN/InstanceNorm gradient
-    amplifies rounding ~1000x — the fp32 oracle itself is only good to 1e-2 here)."""
-    model, cfg, (T, R, Ds), (A, B) = H.build_case(name, precision=precision)
+    fp64.  The yardstick is the error the REFERENCE's own arithmetic makes on the same problem:
+      fp32 engine: error <= 4x the error of the fp32 oracle (floor 1e-3);
+      bf16 engine: error <= 1.25x the error of the oracle under torch.autocast(bfloat16) (floor 0.1) — the LSGAN
+      gradient through InstanceNorm is common-mode dominated, so ANY bf16 arithmetic loses most of it (the
+      reference under autocast is 85-160 % off on netT/netR here; measured, see DESIGN.md "Parity")."""
+    model, cfg, (T, R, Ds), (A, B) = H.build_case(name, precision=precision, conv_engine=engine)
     H.run_engine_steps(model, A, B, 1)
     truth = _oracle_grads(cfg, T, R, Ds, A, B, torch.float64)
-    ref32 = _oracle_grads(cfg, T, R, Ds, A, B, torch.float32)
-    bad = []
+    if precision == "fp32":
+        yard, factor, floor = _oracle_grads(cfg, T, R, Ds, A, B, torch.float32), 4.0, 1e-3
+    else:
+        yard, factor, floor = _oracle_grads(cfg, T, R, Ds, A, B, torch.float32, autocast=True), 1.25, 0.1
+    bad, summary = [], {}
     for tag, net in (("R", model.netR), ("T", model.netT), ("D", model.netD)):
+        errs = []
         for i, (k, p) in enumerate(net.named_parameters()):
             if not k.endswith(".weight"):
                 continue     # biases feeding an InstanceNorm have zero true gradient (rounding noise in any arithmetic)
             t = truth[tag][i]
             nrm = float(t.norm()) + 1e-30
             e_eng = float((p.grad.detach().double().cpu() - t).norm()) / nrm
-            e_ref = float((ref32[tag][i] - t).norm()) / nrm
+            e_ref = float((yard[tag][i] - t).norm()) / nrm
+            errs.append((e_eng, e_ref))
             if e_eng > max(factor * e_ref, floor):
                 bad.append((e_eng, e_ref, tag, k))
-    msg = "\n".join("%s.%s engine err %.3e, fp32-oracle err %.3e" % (t, k, a, b) for a, b, t, k in sorted(bad, reverse=True)[:30])
+        summary[tag] = (float(np.median([a for a, _ in errs])), float(np.median([b for _, b in errs])))
+    print("median gradient error vs fp64 truth (engine, reference-arithmetic yardstick):", summary)
+    msg = "\n".join("%s.%s engine err %.3e, yardstick err %.3e" % (t, k, a, b) for a, b, t, k in sorted(bad, reverse=True)[:30])
     assert not bad, "gradients less accurate than allowed (worst first):\n" + msg
