@@ -131,7 +131,7 @@ def run_engine(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms)
 
-    for _ in range(max(args.warmup, 3)):
+    for _ in range(args.warmup if args.profile else max(args.warmup, 3)):
         model.set_input(dev_batch)
         model.optimize_parameters()
     torch.cuda.synchronize()
@@ -322,6 +322,8 @@ def main():
     ap.add_argument("--no_cpu_baseline", action="store_true")
     ap.add_argument("--kernel_timing", type=int, default=1, help="time conv launches with CUDA events (roofline)")
     ap.add_argument("--grid_sample_bench", type=int, default=1)
+    ap.add_argument("--profile", action="store_true", help="for ncu runs: honour --warmup below 3 (numbers printed under a "
+                                                           "profiler are never bench values)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
