@@ -122,11 +122,12 @@ int nemar_norm_act_fwd(const nemar_tensor* x, const float* stats /* NULL: no nor
 int nemar_norm_act_bwd_reduce(const nemar_tensor* x, const float* stats, int act,
                               const nemar_tensor* dy, int pad_mode, float* red, void* stream);
 /* phase B: dx = rstd*(g - mean(g) - xhat*mean(g*xhat)) (or g when stats==NULL);
- *          dres (optional) (=|+=) fold(dy) */
+ *          dres (optional) (=|+=) fold(dy);  db (optional, [c] floats, overwritten) = sum over n,h,w of dx —
+ *          the bias gradient of the convolution that produced x, fused into this pass */
 int nemar_norm_act_bwd_apply(const nemar_tensor* x, const float* stats, int act,
                              const nemar_tensor* dy, int pad_mode, const float* red,
                              const nemar_tensor* dx, const nemar_tensor* dres, int dres_accumulate,
-                             void* stream);
+                             float* db, void* stream);
 /* dx = dy * act'(y) for an activation fused in a conv epilogue (uses the OUTPUT y) */
 int nemar_act_bwd(const nemar_tensor* y, const nemar_tensor* dy, int act, const nemar_tensor* dx,
                   void* stream);

@@ -24,6 +24,7 @@
 #include "conv_internal.cuh"
 #include "tc_common.cuh"
 
+#include <cstdlib>
 #include <mutex>
 
 using namespace tc;
@@ -116,7 +117,9 @@ template <int BN, int BK>
 struct GatherCfg {
   static constexpr uint32_t A_BYTES = round1k(BM * BK * 2), B_BYTES = round1k(BN * BK * 2);
   static constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES_RAW = (int)(98304u / STAGE_BYTES);
+  // BN <= 128: ~96 KB of stages so that two CTAs share an SM (one's epilogue overlaps the other's main loop);
+  // BN == 256: one CTA per SM with a deep ring (halves the A re-reads per output channel)
+  static constexpr int STAGES_RAW = (int)((BN == 256 ? 196608u : 98304u) / STAGE_BYTES);
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : (STAGES_RAW < 2 ? 2 : STAGES_RAW);
   static constexpr uint32_t TX_BYTES = BM * BK * 2 + BN * BK * 2;
   static constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
@@ -281,7 +284,11 @@ static bool tc_view_ok(const nemar_tensor* t, bool allow_f32) {
   return dt_ok && t->c % 16 == 0 && t->cs % 8 == 0 && t->coff % 8 == 0 && ((((uintptr_t)t->ptr) & 15) == 0);
 }
 
-static int gather_bn(int cd) { return (cd % 128 == 0) ? 128 : ((cd % 64 == 0) ? 64 : ((cd % 32 == 0) ? 32 : 16)); }
+static int gather_bn(int cd, int bk, bool f32) {
+  static const int wide = [] { const char* e = getenv("NEMAR_TC_WIDE"); return e ? atoi(e) : 0; }();
+  if (wide && cd % 256 == 0 && bk == 64 && !f32) return 256;
+  return (cd % 128 == 0) ? 128 : ((cd % 64 == 0) ? 64 : ((cd % 32 == 0) ? 32 : 16));
+}
 
 }  // namespace
 
@@ -304,9 +311,9 @@ int tc_gather_gemm(const nemar_tensor* src_in, const nemar_tensor* dst_in, const
   nemar_tensor src = *src_in, dst = *dst_in;
   src.h += 2 * src.pad; src.w += 2 * src.pad; src.pad = 0;
   dst.h += 2 * dst.pad; dst.w += 2 * dst.pad; dst.pad = 0;
-  const int BN = gather_bn(dst.c);
   const int BK = chunk_for(src.c);
   const bool f32 = dst.dtype == NEMAR_F32;
+  const int BN = gather_bn(dst.c, BK, f32);
   const int esz = f32 ? 4 : 2;
   const int taps_total = gg.kh * gg.kw;
   CUtensorMap tmB;
@@ -354,6 +361,7 @@ int tc_gather_gemm(const nemar_tensor* src_in, const nemar_tensor* dst_in, const
     if (rc) return rc;
     const int ctiles = (dst.c + BN - 1) / BN;
     switch (BN) {
+      case 256: rc = launch_gather_t<256, 64, false>(tmA, tmB, P, ctiles, s); break;
       case 128: rc = launch_gather_k<128>(tmA, tmB, P, ctiles, BK, f32, s); break;
       case 64: rc = launch_gather_k<64>(tmA, tmB, P, ctiles, BK, f32, s); break;
       case 32: rc = launch_gather_k<32>(tmA, tmB, P, ctiles, BK, f32, s); break;
@@ -381,7 +389,9 @@ struct WgradParams {
   int tiles_per_split;            // pixel tiles handled by one CTA
   int stride, kw, pe;
   int co_tiles, ci_tiles, taps;
-  int ci;                         // channels of x (row length of the partial buffer)
+  int ci;                         // channels of the N operand (row length of the partial buffer)
+  int m_channels;                 // channels of the M operand (chunks beyond it are neither loaded nor used)
+  int shift_on_a;                 // 0: A = dY, B = X (tap-shifted);  1 (swapped roles): A = X (tap-shifted), B = dY
   float* partial;                 // [split][tap][co_tiles*128][ci]
 };
 
@@ -447,14 +457,19 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant_
         const int x0 = tx * P.tw, y0 = ty * P.th, n0 = tn * P.tn;
         mbar_wait(&empty_bar[stage], phase ^ 1);
         uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
-        mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+        // channel chunks of the M operand beyond its extent feed accumulator rows nobody reads: skip their loads
+        int na = (P.m_channels - cot * BM + CA - 1) / CA;
+        if (na > Cfg::NA) na = Cfg::NA;
+        mbar_expect_tx(&full_bar[stage], (uint32_t)na * Cfg::CHUNK_A + Cfg::B_BYTES);
+        const int xs = x0 * P.stride - P.pe + tb, ys = y0 * P.stride - P.pe + ta;   // tap-shifted box of X
+        const int xa = P.shift_on_a ? xs : x0, ya = P.shift_on_a ? ys : y0;
+        const int xb = P.shift_on_a ? x0 : xs, yb = P.shift_on_a ? y0 : ys;
 #pragma unroll
         for (int c = 0; c < Cfg::NA; ++c)
-          tma_load_4d(sa + c * Cfg::CHUNK_A, &tmDY, &full_bar[stage], cot * BM + c * CA, x0, y0, n0);
+          if (c < na) tma_load_4d(sa + c * Cfg::CHUNK_A, &tmDY, &full_bar[stage], cot * BM + c * CA, xa, ya, n0);
 #pragma unroll
         for (int c = 0; c < Cfg::NB; ++c)
-          tma_load_4d(sa + Cfg::A_BYTES + c * Cfg::CHUNK_B, &tmX, &full_bar[stage], cit * BN + c * CB,
-                      x0 * P.stride - P.pe + tb, y0 * P.stride - P.pe + ta, n0);
+          tma_load_4d(sa + Cfg::A_BYTES + c * Cfg::CHUNK_B, &tmX, &full_bar[stage], cit * BN + c * CB, xb, yb, n0);
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
@@ -511,23 +526,27 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant_
 }
 
 // dw[co][ci][tap] = sum_split partial[split][tap][co][ci]   (co < co_real, ci < ci_real)
+// partial is [split][tap][m_pad][n_pad]; (m,n) = (co,ci), or (ci,co) when the operand roles were swapped
 __global__ void wgrad_finalize_kernel(const float* __restrict__ partial, float* __restrict__ dw, int splits, int taps,
-                                      int co_real, int co_pad, int ci_real, int ci_pad) {
+                                      int co_real, int ci_real, int m_pad, int n_pad, int swapped) {
   const int64_t total = (int64_t)co_real * ci_real * taps;
+  const int n_real = swapped ? co_real : ci_real;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    int c_i = (int)(i % ci_real);          // ci fastest: coalesced partial reads
-    int64_t r = i / ci_real;
+    int nn = (int)(i % n_real);            // N fastest: coalesced partial reads
+    int64_t r = i / n_real;
     int tap = (int)(r % taps);
-    int c_o = (int)(r / taps);
+    int mm = (int)(r / taps);
     float acc = 0.f;
     for (int s = 0; s < splits; ++s)
-      acc += __ldg(partial + (((int64_t)s * taps + tap) * co_pad + c_o) * ci_pad + c_i);
+      acc += __ldg(partial + (((int64_t)s * taps + tap) * m_pad + mm) * n_pad + nn);
+    const int c_o = swapped ? nn : mm, c_i = swapped ? mm : nn;
     dw[((int64_t)c_o * ci_real + c_i) * taps + tap] = acc;
   }
 }
 
 struct WgradPlan {
   int CA, CB, BN, tw, th, tn, tiles_x, tiles_y, tiles_n, splits, tiles_per_split, co_tiles, ci_tiles, taps;
+  int swapped;      // 1: M operand = X (input channels), N operand = dY — for heads with few output channels
   int64_t ws_bytes;
 };
 
@@ -540,15 +559,19 @@ static bool wgrad_bn(int c, int& cb, int& bn) {
 }
 
 static bool plan_wgrad(const nemar_tensor* x, const nemar_tensor* dy, int kh, int kw, WgradPlan& p) {
-  if (!wgrad_bn(x->c, p.CB, p.BN)) return false;
-  p.CA = chunk_for(dy->c);
+  // the MMA cost scales with N and the accumulator has 128 M rows regardless: put the SMALLER channel count on N
+  p.swapped = (dy->c <= 32 && dy->c < x->c) ? 1 : 0;
+  const nemar_tensor* mop = p.swapped ? x : dy;      // M operand
+  const nemar_tensor* nop = p.swapped ? dy : x;      // N operand
+  if (!wgrad_bn(nop->c, p.CB, p.BN)) return false;
+  p.CA = chunk_for(mop->c);
   pick_tile(dy->w, dy->h, p.tw, p.th, p.tn, WG_KP);
   p.tiles_x = (dy->w + p.tw - 1) / p.tw;
   p.tiles_y = (dy->h + p.th - 1) / p.th;
   p.tiles_n = (dy->n + p.tn - 1) / p.tn;
   p.taps = kh * kw;
-  p.co_tiles = (dy->c + BM - 1) / BM;
-  p.ci_tiles = x->c / p.BN;
+  p.co_tiles = (mop->c + BM - 1) / BM;
+  p.ci_tiles = nop->c / p.BN;
   const int total = p.tiles_x * p.tiles_y * p.tiles_n;
   const int base = p.taps * p.co_tiles * p.ci_tiles;
   int splits = (148 * 2 + base - 1) / base;        // ~2 CTAs per SM in flight
@@ -556,7 +579,7 @@ static bool plan_wgrad(const nemar_tensor* x, const nemar_tensor* dy, int kh, in
   if (splits < 1) splits = 1;
   p.tiles_per_split = (total + splits - 1) / splits;
   p.splits = (total + p.tiles_per_split - 1) / p.tiles_per_split;
-  p.ws_bytes = (int64_t)p.splits * p.taps * p.co_tiles * BM * x->c * 4;
+  p.ws_bytes = (int64_t)p.splits * p.taps * p.co_tiles * BM * nop->c * 4;
   return true;
 }
 
@@ -617,10 +640,12 @@ int tc_wgrad(const nemar_tensor* x_in, const nemar_tensor* dy, float* dw, int co
   plan_wgrad(&x, dy, kh, kw, pl);
   NEMAR_REQUIRE(workspace && workspace_bytes >= pl.ws_bytes, "tc_wgrad: workspace too small (%lld < %lld)",
                 (long long)workspace_bytes, (long long)pl.ws_bytes);
-  CUtensorMap tmDY, tmX;
-  int rc = make_act_map(&tmDY, dy, pl.CA, pl.tw, pl.th, pl.tn, 1);
+  CUtensorMap tmDY, tmX;   // named after the default roles: first = M operand (A), second = N operand (B)
+  int rc = pl.swapped ? make_act_map(&tmDY, &x, pl.CA, pl.tw, pl.th, pl.tn, stride)
+                      : make_act_map(&tmDY, dy, pl.CA, pl.tw, pl.th, pl.tn, 1);
   if (rc) return rc;
-  rc = make_act_map(&tmX, &x, pl.CB, pl.tw, pl.th, pl.tn, stride);
+  rc = pl.swapped ? make_act_map(&tmX, dy, pl.CB, pl.tw, pl.th, pl.tn, 1)
+                  : make_act_map(&tmX, &x, pl.CB, pl.tw, pl.th, pl.tn, stride);
   if (rc) return rc;
   WgradParams P;
   P.tw = pl.tw; P.th = pl.th; P.tn = pl.tn;
@@ -628,7 +653,9 @@ int tc_wgrad(const nemar_tensor* x_in, const nemar_tensor* dy, float* dw, int co
   P.tiles_per_split = pl.tiles_per_split;
   P.stride = stride; P.kw = kw; P.pe = pe;
   P.co_tiles = pl.co_tiles; P.ci_tiles = pl.ci_tiles; P.taps = pl.taps;
-  P.ci = x.c;
+  P.ci = pl.swapped ? dy->c : x.c;
+  P.m_channels = pl.swapped ? x.c : dy->c;
+  P.shift_on_a = pl.swapped;
   P.partial = (float*)workspace;
   if (pl.CA == 64) rc = launch_wgrad_a<64>(tmDY, tmX, P, pl, s);
   else if (pl.CA == 32) rc = launch_wgrad_a<32>(tmDY, tmX, P, pl, s);
@@ -636,7 +663,7 @@ int tc_wgrad(const nemar_tensor* x_in, const nemar_tensor* dy, float* dw, int co
   if (rc) return rc;
   const int64_t total = (int64_t)co_real * ci_real * pl.taps;
   wgrad_finalize_kernel<<<grid_for(total, 256), 256, 0, s>>>((const float*)workspace, dw, pl.splits, pl.taps, co_real,
-                                                              pl.co_tiles * BM, ci_real, x.c);
+                                                              ci_real, pl.co_tiles * BM, P.ci, pl.swapped);
   NEMAR_LAUNCH_CHECK();
   return 0;
 }

@@ -277,6 +277,9 @@ plane_reduce_kernel(TView x, const float* __restrict__ stats, int act, TView dy,
 #pragma unroll
   for (int k = 0; k < V; ++k) { a0[k] = 0.f; a1[k] = 0.f; }
   int my_cg = threadIdx.x % G;
+  float hmean[V], hrstd[V];
+  if (MODE == 1 && reg_path) load_mean_rstd<V>(stats, nn, c, my_cg * V, inv_hw, hmean, hrstd);
+#pragma unroll 2
   for (int64_t j = lo + threadIdx.x; j < hi; j += blockDim.x) {
     int cg = (int)(j % G);
     int64_t p = j / G;
@@ -292,7 +295,12 @@ plane_reduce_kernel(TView x, const float* __restrict__ stats, int act, TView dy,
       float g[V];
       load_fold<T, V>(dy, nn, yy, xx, cg * V, pad_mode, g);
       float mean[V], rstd[V];
-      load_mean_rstd<V>(stats, nn, c, cg * V, inv_hw, mean, rstd);
+      if (reg_path) {
+#pragma unroll
+        for (int k = 0; k < V; ++k) { mean[k] = hmean[k]; rstd[k] = hrstd[k]; }
+      } else {
+        load_mean_rstd<V>(stats, nn, c, cg * V, inv_hw, mean, rstd);
+      }
 #pragma unroll
       for (int k = 0; k < V; ++k) {
         float xh = (v[k] - mean[k]) * rstd[k];
@@ -429,15 +437,20 @@ template <typename T, int V>
 __global__ void __launch_bounds__(256)
 norm_act_fwd_kernel(TView x, const float* __restrict__ stats, int act, TView res, int has_res, TView y,
                     int pad_mode, float inv_hw) {
+  // grid = (chunks, n).  Items of one sample = padded destination positions x channel groups; when the block size
+  // is a multiple of the group count every thread keeps ONE channel group, so mean/rstd are computed once.
+  const int nn = blockIdx.y;
   const int G = y.c / V;
-  const int64_t total = (int64_t)y.n * y.hp * y.wp * G;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
-       i += (int64_t)gridDim.x * blockDim.x) {
+  const int64_t items = (int64_t)y.hp * y.wp * G;
+  const bool fixed = (blockDim.x % G) == 0 && ((int64_t)gridDim.x * blockDim.x) % G == 0;
+  float hmean[V], hrstd[V];
+  if (stats && fixed) load_mean_rstd<V>(stats, nn, y.c, (int)(threadIdx.x % G) * V, inv_hw, hmean, hrstd);
+#pragma unroll 2
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < items; i += (int64_t)gridDim.x * blockDim.x) {
     int cg = (int)(i % G);
     int64_t r = i / G;
-    int xp = (int)(r % y.wp); r /= y.wp;
-    int yp = (int)(r % y.hp);
-    int nn = (int)(r / y.hp);
+    int xp = (int)(r % y.wp);
+    int yp = (int)(r / y.wp);
     int ys = yp - y.pad, xs = xp - y.pad;
     bool halo = ys < 0 || ys >= y.h || xs < 0 || xs >= y.w;
     float v[V];
@@ -450,7 +463,12 @@ norm_act_fwd_kernel(TView x, const float* __restrict__ stats, int act, TView res
       ldv<T, V>((const T*)x.ptr + x.pix(nn, ys, xs) + cg * V, v);
       if (stats) {
         float mean[V], rstd[V];
-        load_mean_rstd<V>(stats, nn, y.c, cg * V, inv_hw, mean, rstd);
+        if (fixed) {
+#pragma unroll
+          for (int k = 0; k < V; ++k) { mean[k] = hmean[k]; rstd[k] = hrstd[k]; }
+        } else {
+          load_mean_rstd<V>(stats, nn, y.c, cg * V, inv_hw, mean, rstd);
+        }
 #pragma unroll
         for (int k = 0; k < V; ++k) v[k] = (v[k] - mean[k]) * rstd[k];
       }
@@ -467,6 +485,14 @@ norm_act_fwd_kernel(TView x, const float* __restrict__ stats, int act, TView res
   }
 }
 
+static int plane_chunks(int64_t items_per_sample, int n) {
+  int64_t chunks = (items_per_sample + 256 * 8 - 1) / (256 * 8);
+  int64_t cap = (148 * 16 + n - 1) / n;
+  if (chunks > cap) chunks = cap;
+  if (chunks < 1) chunks = 1;
+  return (int)chunks;
+}
+
 NEMAR_API int nemar_norm_act_fwd(const nemar_tensor* x, const float* stats, int act,
                                  const nemar_tensor* residual, const nemar_tensor* y, int pad_mode,
                                  void* stream) {
@@ -481,13 +507,13 @@ NEMAR_API int nemar_norm_act_fwd(const nemar_tensor* x, const float* stats, int 
     constexpr int VV = VecTraits<T>::V;
     bool vec = view_vec_ok<T>(x) && view_vec_ok<T>(y) && (!residual || view_vec_ok<T>(residual));
     if (vec) {
-      int64_t total = (int64_t)yv.n * yv.hp * yv.wp * (yv.c / VV);
-      norm_act_fwd_kernel<T, VV><<<grid_for(total, 256), 256, 0, s>>>(xv, stats, act, rv, residual != nullptr,
-                                                                       yv, pad_mode, inv_hw);
+      int64_t items = (int64_t)yv.hp * yv.wp * (yv.c / VV);
+      norm_act_fwd_kernel<T, VV><<<dim3(plane_chunks(items, yv.n), yv.n), 256, 0, s>>>(xv, stats, act, rv, residual != nullptr,
+                                                                                          yv, pad_mode, inv_hw);
     } else {
-      int64_t total = (int64_t)yv.n * yv.hp * yv.wp * yv.c;
-      norm_act_fwd_kernel<T, 1><<<grid_for(total, 256), 256, 0, s>>>(xv, stats, act, rv, residual != nullptr,
-                                                                      yv, pad_mode, inv_hw);
+      int64_t items = (int64_t)yv.hp * yv.wp * yv.c;
+      norm_act_fwd_kernel<T, 1><<<dim3(plane_chunks(items, yv.n), yv.n), 256, 0, s>>>(xv, stats, act, rv, residual != nullptr,
+                                                                                         yv, pad_mode, inv_hw);
     }
   });
   NEMAR_LAUNCH_CHECK();
@@ -498,16 +524,34 @@ template <typename T, int V>
 __global__ void __launch_bounds__(256)
 norm_act_bwd_apply_kernel(TView x, const float* __restrict__ stats, int act, TView dy, int pad_mode,
                           const float* __restrict__ red, TView dx, TView dres, int has_dres,
-                          int dres_acc, float inv_hw) {
+                          int dres_acc, float inv_hw, float* __restrict__ db) {
+  // grid = (chunks, n); thread keeps one channel group when blockDim % G == 0 (statistics hoisted, bias-gradient
+  // column sums kept in registers and flushed with one shared + one global atomic per channel per block).
+  extern __shared__ float sdb[];   // [c] when db != nullptr
+  const int nn = blockIdx.y;
   const int G = x.c / V;
-  const int64_t total = (int64_t)x.n * x.h * x.w * G;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
-       i += (int64_t)gridDim.x * blockDim.x) {
+  const int64_t items = (int64_t)x.h * x.w * G;
+  const bool fixed = (blockDim.x % G) == 0 && ((int64_t)gridDim.x * blockDim.x) % G == 0;
+  const int my_cg = (int)(threadIdx.x % G);
+  if (db) {
+    for (int k = threadIdx.x; k < x.c; k += blockDim.x) sdb[k] = 0.f;
+    __syncthreads();
+  }
+  float hmean[V], hrstd[V], hm1[V], hm2[V], bsum[V];
+#pragma unroll
+  for (int k = 0; k < V; ++k) bsum[k] = 0.f;
+  if (stats && fixed) {
+    load_mean_rstd<V>(stats, nn, x.c, my_cg * V, inv_hw, hmean, hrstd);
+    const float* rd = red + ((int64_t)nn * x.c + my_cg * V) * 2;
+#pragma unroll
+    for (int k = 0; k < V; ++k) { hm1[k] = __ldg(rd + 2 * k) * inv_hw; hm2[k] = __ldg(rd + 2 * k + 1) * inv_hw; }
+  }
+#pragma unroll 2
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < items; i += (int64_t)gridDim.x * blockDim.x) {
     int cg = (int)(i % G);
     int64_t r = i / G;
-    int xx = (int)(r % x.w); r /= x.w;
-    int yy = (int)(r % x.h);
-    int nn = (int)(r / x.h);
+    int xx = (int)(r % x.w);
+    int yy = (int)(r / x.w);
     float g[V], v[V], o[V];
     load_fold<T, V>(dy, nn, yy, xx, cg * V, pad_mode, g);
     if (has_dres) {
@@ -525,28 +569,51 @@ norm_act_bwd_apply_kernel(TView x, const float* __restrict__ stats, int act, TVi
     }
     ldv<T, V>((const T*)x.ptr + x.pix(nn, yy, xx) + cg * V, v);
     if (stats) {
-      float mean[V], rstd[V];
-      load_mean_rstd<V>(stats, nn, x.c, cg * V, inv_hw, mean, rstd);
-      const float* rd = red + ((int64_t)nn * x.c + cg * V) * 2;
+      float mean[V], rstd[V], m1[V], m2[V];
+      if (fixed) {
+#pragma unroll
+        for (int k = 0; k < V; ++k) { mean[k] = hmean[k]; rstd[k] = hrstd[k]; m1[k] = hm1[k]; m2[k] = hm2[k]; }
+      } else {
+        load_mean_rstd<V>(stats, nn, x.c, cg * V, inv_hw, mean, rstd);
+        const float* rd = red + ((int64_t)nn * x.c + cg * V) * 2;
+#pragma unroll
+        for (int k = 0; k < V; ++k) { m1[k] = __ldg(rd + 2 * k) * inv_hw; m2[k] = __ldg(rd + 2 * k + 1) * inv_hw; }
+      }
 #pragma unroll
       for (int k = 0; k < V; ++k) {
         float xh = (v[k] - mean[k]) * rstd[k];
         float gg = g[k] * act_grad_from_x(xh, act);
-        float m1 = __ldg(rd + 2 * k) * inv_hw, m2 = __ldg(rd + 2 * k + 1) * inv_hw;
-        o[k] = rstd[k] * (gg - m1 - xh * m2);
+        o[k] = rstd[k] * (gg - m1[k] - xh * m2[k]);
       }
     } else {
 #pragma unroll
       for (int k = 0; k < V; ++k) o[k] = g[k] * act_grad_from_x(v[k], act);
     }
     stv<T, V>((T*)dx.ptr + dx.pix(nn, yy, xx) + cg * V, o);
+    if (db) {
+      if (fixed) {
+#pragma unroll
+        for (int k = 0; k < V; ++k) bsum[k] += o[k];
+      } else {
+#pragma unroll
+        for (int k = 0; k < V; ++k) atomicAdd(&sdb[cg * V + k], o[k]);
+      }
+    }
+  }
+  if (db) {
+    if (fixed) {
+#pragma unroll
+      for (int k = 0; k < V; ++k) atomicAdd(&sdb[my_cg * V + k], bsum[k]);
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < x.c; k += blockDim.x) atomicAdd(db + k, sdb[k]);
   }
 }
 
 NEMAR_API int nemar_norm_act_bwd_apply(const nemar_tensor* x, const float* stats, int act,
                                        const nemar_tensor* dy, int pad_mode, const float* red,
                                        const nemar_tensor* dx, const nemar_tensor* dres, int dres_accumulate,
-                                       void* stream) {
+                                       float* db, void* stream) {
   NEMAR_REQUIRE(view_ok(x) && view_ok(dy) && view_ok(dx) && same_shape(x, dy) && same_shape(x, dx) &&
                     x->dtype == dy->dtype && x->dtype == dx->dtype,
                 "norm_act_bwd_apply: mismatch");
@@ -559,14 +626,16 @@ NEMAR_API int nemar_norm_act_bwd_apply(const nemar_tensor* x, const float* stats
   DISPATCH_DTYPE(xv.dtype, T, {
     constexpr int VV = VecTraits<T>::V;
     bool vec = view_vec_ok<T>(x) && view_vec_ok<T>(dy) && view_vec_ok<T>(dx) && (!dres || view_vec_ok<T>(dres));
+    size_t smem = db ? sizeof(float) * xv.c : 0;
+    if (db) cudaMemsetAsync(db, 0, sizeof(float) * xv.c, s);
     if (vec) {
-      int64_t total = (int64_t)xv.n * xv.h * xv.w * (xv.c / VV);
-      norm_act_bwd_apply_kernel<T, VV><<<grid_for(total, 256), 256, 0, s>>>(
-          xv, stats, act, dyv, pad_mode, red, dxv, dr, dres != nullptr, dres_accumulate, inv_hw);
+      int64_t items = (int64_t)xv.h * xv.w * (xv.c / VV);
+      norm_act_bwd_apply_kernel<T, VV><<<dim3(plane_chunks(items, xv.n), xv.n), 256, smem, s>>>(
+          xv, stats, act, dyv, pad_mode, red, dxv, dr, dres != nullptr, dres_accumulate, inv_hw, db);
     } else {
-      int64_t total = (int64_t)xv.n * xv.h * xv.w * xv.c;
-      norm_act_bwd_apply_kernel<T, 1><<<grid_for(total, 256), 256, 0, s>>>(
-          xv, stats, act, dyv, pad_mode, red, dxv, dr, dres != nullptr, dres_accumulate, inv_hw);
+      int64_t items = (int64_t)xv.h * xv.w * xv.c;
+      norm_act_bwd_apply_kernel<T, 1><<<dim3(plane_chunks(items, xv.n), xv.n), 256, smem, s>>>(
+          xv, stats, act, dyv, pad_mode, red, dxv, dr, dres != nullptr, dres_accumulate, inv_hw, db);
     }
   });
   NEMAR_LAUNCH_CHECK();

@@ -128,12 +128,14 @@ class ConvCfg:
     (zero-padded to a multiple of 16 on the tensor-core engine); the input tensor brings its own padding."""
 
     def __init__(self, cin, cout, k, stride=1, pad=0, transposed=False, x_pad=0, act=L.ACT_NONE, stats=False,
-                 out_f32=False, out_pad_t=0, use_tc=False, cout_p=None):
+                 out_f32=False, out_pad_t=0, use_tc=False, cout_p=None, defer_bias_grad=False):
         self.geom = L.ConvGeom(cin, cout, k, k, stride, pad, int(transposed))
         self.cin, self.cout, self.k, self.stride, self.pad = cin, cout, k, stride, pad
         self.transposed, self.x_pad, self.act, self.stats = transposed, x_pad, act, stats
         self.out_f32, self.out_pad_t, self.use_tc = out_f32, out_pad_t, use_tc
         self.cout_p = cout if cout_p is None else cout_p
+        # True: the bias gradient is produced by the NormActFn consuming this conv's output (fused column sum)
+        self.defer_bias_grad = defer_bias_grad
 
     def out_hw(self, h, w):
         if not self.transposed:
@@ -225,7 +227,7 @@ class Conv2dFn(Function):
                                                             int(cfg.use_tc))
             ws = torch.empty(max(int(ws_bytes), 16), dtype=torch.uint8, device=x.device) if ws_bytes > 0 else None
             call("nemar_conv2d_wgrad", xv, gv, cfg.geom, fptr(dw), vptr(ws), i64(ws_bytes), int(cfg.use_tc), stream())
-        if ctx.has_bias and ctx.needs_input_grad[2]:
+        if ctx.has_bias and ctx.needs_input_grad[2] and not cfg.defer_bias_grad:
             db = torch.empty(cfg.cout_p, dtype=torch.float32, device=x.device)
             call("nemar_bias_grad", view(g), fptr(db), stream())
             db = db[:cfg.cout]
@@ -237,7 +239,9 @@ class Conv2dFn(Function):
 # ------------------------------------------------------------------------------------------------
 class NormActFn(Function):
     @staticmethod
-    def forward(ctx, x, stats, residual, act, res_pad, out_pad, pad_mode):
+    def forward(ctx, x, stats, residual, act, res_pad, out_pad, pad_mode, bias=None):
+        """`bias` (optional) is the bias Parameter of the conv that produced x: it takes no part in the forward,
+        but its gradient (= column sums of dx) is produced by this op's backward pass for free."""
         x = _c(x)
         n, h, w, c = x.shape
         y = torch.empty((n, h + 2 * out_pad, w + 2 * out_pad, c), dtype=x.dtype, device=x.device)
@@ -246,13 +250,14 @@ class NormActFn(Function):
             residual = _c(residual)
             rv = view(residual, res_pad)
         call("nemar_norm_act_fwd", view(x), fptr(stats), act, rv, view(y, out_pad), pad_mode, stream())
-        ctx.meta = (act, res_pad, out_pad, pad_mode, residual.shape if residual is not None else None)
+        ctx.meta = (act, res_pad, out_pad, pad_mode, residual.shape if residual is not None else None,
+                    bias.numel() if bias is not None else 0)
         ctx.save_for_backward(x, stats)
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        act, res_pad, out_pad, pad_mode, res_shape = ctx.meta
+        act, res_pad, out_pad, pad_mode, res_shape, nbias = ctx.meta
         x, stats = ctx.saved_tensors
         dy = _c(dy)
         n, h, w, c = x.shape
@@ -266,9 +271,13 @@ class NormActFn(Function):
         if res_shape is not None and ctx.needs_input_grad[2]:
             dres = (torch.zeros if res_pad > 0 else torch.empty)(res_shape, dtype=x.dtype, device=x.device)
             drv = view(dres, res_pad)
+        # the bias gradient of the conv that produced x is the column sum of dx: fused into this pass
+        db = None
+        if nbias and ctx.needs_input_grad[7]:
+            db = torch.empty(c, dtype=torch.float32, device=x.device)
         call("nemar_norm_act_bwd_apply", view(x), fptr(stats), act, view(dy, out_pad), pad_mode, fptr(red), view(dx),
-             drv, 0, stream())
-        return dx, None, dres, None, None, None, None
+             drv, 0, fptr(db), stream())
+        return dx, None, dres, None, None, None, None, (db[:nbias] if db is not None else None)
 
 
 class MaxPool2Fn(Function):

@@ -55,34 +55,36 @@ class Conv(nn.Module):
         cin, cout, k, s, p, t, _ = self.meta
         return "%d->%d k%d s%d p%d%s" % (cin, cout, k, s, p, " transposed" if t else "")
 
-    def run(self, x, x_pad=0, act=L.ACT_NONE, stats=False, out_f32=False):
+    def run(self, x, x_pad=0, act=L.ACT_NONE, stats=False, out_f32=False, defer_bias_grad=False):
         cin, cout, k, stride, pad, transposed, opt = self.meta
-        key = (x_pad, act, stats, out_f32, x.dtype, CONFIG.conv_engine, x.shape[3])
+        key = (x_pad, act, stats, out_f32, x.dtype, CONFIG.conv_engine, x.shape[3], defer_bias_grad)
         cfg = self._cfgs.get(key)
         if cfg is None:
             use_tc = tc_policy(cin, cout, k, stride, transposed, x.dtype, x.shape[3])
             cout_p = (cout + 15) // 16 * 16 if use_tc else cout
-            cfg = F.ConvCfg(cin, cout, k, stride, pad, transposed, x_pad, act, stats, out_f32, opt, use_tc, cout_p)
+            cfg = F.ConvCfg(cin, cout, k, stride, pad, transposed, x_pad, act, stats, out_f32, opt, use_tc, cout_p,
+                            defer_bias_grad and self.bias is not None)
             self._cfgs[key] = cfg
         return F.Conv2dFn.apply(x, self.weight, self.bias, cfg, self._packed)
 
 
-def norm_act(x, stats, act, residual=None, res_pad=0, out_pad=0, pad_mode=L.PAD_REFLECT):
-    return F.NormActFn.apply(x, stats, residual, act, res_pad, out_pad, pad_mode)
+def norm_act(x, stats, act, residual=None, res_pad=0, out_pad=0, pad_mode=L.PAD_REFLECT, bias=None):
+    return F.NormActFn.apply(x, stats, residual, act, res_pad, out_pad, pad_mode, bias)
 
 
 def conv_in_act(conv, x, x_pad, act, out_pad=0, residual=None, res_pad=0):
-    """conv -> InstanceNorm (statistics from the conv epilogue) -> act (+residual) -> optional reflect halo"""
-    y, st = conv.run(x, x_pad=x_pad, stats=True)
-    return norm_act(y, st, act, residual, res_pad, out_pad)
+    """conv -> InstanceNorm (statistics from the conv epilogue) -> act (+residual) -> optional reflect halo.
+    The conv's bias gradient is produced by the norm pass's backward (fused column sum)."""
+    y, st = conv.run(x, x_pad=x_pad, stats=True, defer_bias_grad=True)
+    return norm_act(y, st, act, residual, res_pad, out_pad, bias=conv.bias)
 
 
 def conv_act(conv, x, x_pad, act, out_pad=0, out_f32=False):
     """conv -> act with no normalisation; a reflect halo on the result needs the separate pass"""
     if out_pad == 0:
         return conv.run(x, x_pad=x_pad, act=act, out_f32=out_f32)
-    y = conv.run(x, x_pad=x_pad)
-    return norm_act(y, None, act, None, 0, out_pad)
+    y = conv.run(x, x_pad=x_pad, defer_bias_grad=True)
+    return norm_act(y, None, act, None, 0, out_pad, bias=conv.bias)
 
 
 class ResnetBlock(nn.Module):

@@ -178,12 +178,15 @@ def test_norm_act_fwd_bwd(prec, act, c, h, w, out_pad, res):
     re_ = nhwc(r, dt, 1).requires_grad_(True) if res else None     # residual arrives with its own reflect halo
     stats = torch.zeros(n, c, 2, device=DEV)
     L.call("nemar_instnorm_stats", L.view(xe.detach()), L.fptr(stats), L.stream())
-    ye = F.NormActFn.apply(xe, stats, re_, code, 1, out_pad, L.PAD_REFLECT)
+    bias = torch.zeros(c, device=DEV, requires_grad=True)     # receives the fused column-sum (conv bias gradient)
+    ye = F.NormActFn.apply(xe, stats, re_, code, 1, out_pad, L.PAD_REFLECT, bias)
     ftol = dict(fp32=(1e-4, 1e-4), bf16=(1.6e-2, 1.6e-2))[prec]
     close(nchw(ye), yp, *ftol, "norm_act fwd")
     (ye.float() * nhwc(dg, dt).float()).sum().backward()
     btol = dict(fp32=(2e-3, 2e-4), bf16=(3e-2, 3e-2))[prec]
     close(nchw(xe.grad), xr.grad, *btol, "norm_act dx")
+    colsum = nchw(xe.grad).sum((0, 2, 3))
+    close(bias.grad, colsum, 1e-3, 1e-3 * float(nchw(xe.grad).abs().sum((0, 2, 3)).max()) + 1e-6, "fused bias grad")
     if prec == "fp32":
         assert rel_rms(nchw(xe.grad), xr.grad) < 2e-5, "norm_act dx rel-rms %.3e" % rel_rms(nchw(xe.grad), xr.grad)
     if res:
