@@ -73,6 +73,14 @@ int nemar_fill_channels(const nemar_tensor* t, int c0, int nc, void* stream);
 int nemar_copy_view(const nemar_tensor* src, const nemar_tensor* dst, int pad_mode, void* stream);
 /* dst view <- src view with a storage-dtype change (fp32 <-> bf16); same n,h,w,c; interiors only */
 int nemar_cast_view(const nemar_tensor* src, const nemar_tensor* dst, void* stream);
+/* Tap <-> channel transforms that turn the 3-channel k7 head and the 3-channel k7 tail of the generator
+ * (networks.py:349-350,375-376) into 1x1 convolutions for the tensor-core engine (src/dst are plain images,
+ * pad must be 0; out-of-range source pixels read as zero):
+ *   gather_taps: dst[n,y,x,(a*k+b)*c+ch] = src[n, y+sgn*a, x+sgn*b, ch]   (ch < c; channels >= k*k*c are zeroed)
+ *   sum_taps:    dst[n,y,x,ch] = act(bias[ch] + sum_{a,b} src[n, y-sgn*a, x-sgn*b, (a*k+b)*c+ch])   (ch < c) */
+int nemar_gather_taps(const nemar_tensor* src, const nemar_tensor* dst, int k, int c, int sgn, void* stream);
+int nemar_sum_taps(const nemar_tensor* src, const nemar_tensor* dst, int k, int c, int sgn, const float* bias,
+                   int act, void* stream);
 /* dst view (=|+=) src view folded (adjoint of nemar_copy_view) */
 int nemar_copy_view_bwd(const nemar_tensor* dsrc_out, const nemar_tensor* ddst_in, int pad_mode,
                         int accumulate, void* stream);

@@ -553,7 +553,7 @@ struct WgradPlan {
 static bool wgrad_bn(int c, int& cb, int& bn) {
   cb = chunk_for(c);
   if (cb == 64) { bn = (c % 256 == 0) ? 256 : ((c % 128 == 0) ? 128 : 64); return true; }
-  if (cb == 32) { bn = c; return c == 32 || c == 96; }
+  if (cb == 32) { bn = c; return c == 32 || c == 96 || c == 160; }
   bn = c;
   return c == 16;
 }
@@ -606,6 +606,7 @@ static int launch_wgrad_a(const CUtensorMap& d, const CUtensorMap& x, const Wgra
     return launch_wgrad_t<CA, 64, 64>(d, x, P, pl, s);
   }
   if (pl.CB == 32) {
+    if (pl.BN == 160) return launch_wgrad_t<CA, 32, 160>(d, x, P, pl, s);
     if (pl.BN == 96) return launch_wgrad_t<CA, 32, 96>(d, x, P, pl, s);
     return launch_wgrad_t<CA, 32, 32>(d, x, P, pl, s);
   }

@@ -202,6 +202,95 @@ NEMAR_API int nemar_cast_view(const nemar_tensor* src, const nemar_tensor* dst, 
   return 0;
 }
 
+// ---- tap <-> channel transforms (k7 head / tail as 1x1 tensor-core convolutions) ----------------
+__global__ void gather_taps_kernel(TView s, TView d, int k, int c, int sgn) {
+  // one thread -> 8 consecutive destination channels of one pixel (one 16-byte store when d is bf16)
+  const int groups = d.c / 8;
+  const int kc = k * k * c;
+  const int64_t total = (int64_t)d.n * d.h * d.w * groups;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int g = (int)(i % groups);
+    int64_t r = i / groups;
+    int x = (int)(r % d.w); r /= d.w;
+    int y = (int)(r % d.h);
+    int nn = (int)(r / d.h);
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      int oc = g * 8 + j;
+      float val = 0.f;
+      if (oc < kc) {
+        int tap = oc / c, ch = oc - tap * c;
+        int a = tap / k, b = tap - a * k;
+        int sy = y + sgn * a, sx = x + sgn * b;
+        if (sy >= 0 && sy < s.h && sx >= 0 && sx < s.w) val = ld_rt(s.ptr, s.dtype, s.pix(nn, sy, sx) + ch);
+      }
+      v[j] = val;
+    }
+    const int64_t o = d.pix(nn, y, x) + g * 8;
+    if (d.dtype == NEMAR_BF16) {
+      uint4 pk;
+      __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&pk);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) h[j] = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+      *reinterpret_cast<uint4*>((__nv_bfloat16*)d.ptr + o) = pk;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) ((float*)d.ptr)[o + j] = v[j];
+    }
+  }
+}
+
+__global__ void sum_taps_kernel(TView s, TView d, int k, int c, int sgn, const float* __restrict__ bias, int act) {
+  const int64_t total = (int64_t)d.n * d.h * d.w;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int x = (int)(i % d.w);
+    int64_t r = i / d.w;
+    int y = (int)(r % d.h);
+    int nn = (int)(r / d.h);
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};     // c <= 4
+    for (int a = 0; a < k; ++a) {
+      int sy = y - sgn * a;
+      if (sy < 0 || sy >= s.h) continue;
+      for (int b = 0; b < k; ++b) {
+        int sx = x - sgn * b;
+        if (sx < 0 || sx >= s.w) continue;
+        const int64_t base = s.pix(nn, sy, sx) + (a * k + b) * c;
+        for (int ch = 0; ch < c; ++ch) acc[ch] += ld_rt(s.ptr, s.dtype, base + ch);
+      }
+    }
+    const int64_t o = d.pix(nn, y, x);
+    for (int ch = 0; ch < d.c; ++ch) {
+      float v = 0.f;
+      if (ch < c) v = act_fwd(acc[ch] + (bias ? __ldg(bias + ch) : 0.f), act);
+      st_rt(d.ptr, d.dtype, o + ch, v);
+    }
+  }
+}
+
+NEMAR_API int nemar_gather_taps(const nemar_tensor* src, const nemar_tensor* dst, int k, int c, int sgn, void* stream) {
+  NEMAR_REQUIRE(view_ok(src) && view_ok(dst) && src->pad == 0 && dst->pad == 0 && src->n == dst->n, "gather_taps: bad views");
+  NEMAR_REQUIRE(k > 0 && c > 0 && c <= src->c && dst->c % 8 == 0 && dst->c >= k * k * c && (sgn == 1 || sgn == -1) &&
+                    (dst->dtype != NEMAR_BF16 || ((dst->cs % 8 == 0) && (dst->coff % 8 == 0) && ((((uintptr_t)dst->ptr) & 15) == 0))),
+                "gather_taps: bad arguments");
+  TView s = make_view(src), d = make_view(dst);
+  int64_t total = (int64_t)d.n * d.h * d.w * (d.c / 8);
+  gather_taps_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(s, d, k, c, sgn);
+  NEMAR_LAUNCH_CHECK();
+  return 0;
+}
+
+NEMAR_API int nemar_sum_taps(const nemar_tensor* src, const nemar_tensor* dst, int k, int c, int sgn, const float* bias,
+                             int act, void* stream) {
+  NEMAR_REQUIRE(view_ok(src) && view_ok(dst) && src->pad == 0 && dst->pad == 0 && src->n == dst->n, "sum_taps: bad views");
+  NEMAR_REQUIRE(k > 0 && c > 0 && c <= 4 && c <= dst->c && src->c >= k * k * c && (sgn == 1 || sgn == -1), "sum_taps: bad arguments");
+  TView s = make_view(src), d = make_view(dst);
+  int64_t total = (int64_t)d.n * d.h * d.w;
+  sum_taps_kernel<<<grid_for(total, 128), 128, 0, (cudaStream_t)stream>>>(s, d, k, c, sgn, bias, act);
+  NEMAR_LAUNCH_CHECK();
+  return 0;
+}
+
 template <typename T, int V>
 __global__ void copy_view_bwd_kernel(TView ds, TView dd, int pad_mode, int accumulate) {
   // ds: gradient wrt the copy source (written), dd: gradient wrt the (padded) destination (read+fold)

@@ -234,6 +234,62 @@ class Conv2dFn(Function):
         return dx, dw, db, None, None
 
 
+class GatherTapsFn(Function):
+    """dst[n,y,x,(a*k+b)*c+ch] = src[n, y+sgn*a, x+sgn*b, ch] — turns a k x k conv over c (<=4) channels into a
+    1x1 conv over k*k*c channels (generator head, networks.py:349-350)."""
+
+    @staticmethod
+    def forward(ctx, x, k, c, sgn, oh, ow, cp, out_dtype):
+        x = _c(x)
+        n = x.shape[0]
+        out = torch.empty((n, oh, ow, cp), dtype=out_dtype, device=x.device)
+        call("nemar_gather_taps", view(x), view(out), k, c, sgn, stream())
+        ctx.meta = (k, c, sgn, x.shape, x.dtype)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        k, c, sgn, shape, dtype = ctx.meta
+        g = _c(g)
+        dx = torch.empty(shape, dtype=dtype, device=g.device)
+        call("nemar_sum_taps", view(g), view(dx), k, c, sgn, None, L.ACT_NONE, stream())
+        return dx, None, None, None, None, None, None, None
+
+
+class SumTapsFn(Function):
+    """dst[n,y,x,ch] = act(bias[ch] + sum_{a,b} src[n, y-sgn*a, x-sgn*b, (a*k+b)*c+ch]) — the tap sum that completes
+    a k x k conv with c (<=4) output channels computed as a 1x1 conv with k*k*c virtual channels (generator tail,
+    networks.py:375-377)."""
+
+    @staticmethod
+    def forward(ctx, x, bias, k, c, sgn, oh, ow, cp, act):
+        x = _c(x)
+        n = x.shape[0]
+        y = torch.empty((n, oh, ow, cp), dtype=torch.float32, device=x.device)
+        call("nemar_sum_taps", view(x), view(y), k, c, sgn, fptr(bias.detach()) if bias is not None else None, act, stream())
+        ctx.meta = (k, c, sgn, x.shape, x.dtype, act, bias is not None)
+        ctx.save_for_backward(y if act != L.ACT_NONE else None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        k, c, sgn, shape, dtype, act, has_bias = ctx.meta
+        (y,) = ctx.saved_tensors
+        dy = _c(dy)
+        if act != L.ACT_NONE:
+            g = torch.empty_like(dy)
+            call("nemar_act_bwd", view(y), view(dy), act, view(g), stream())
+        else:
+            g = dy
+        db = None
+        if has_bias and ctx.needs_input_grad[1]:
+            db = torch.empty(c, dtype=torch.float32, device=dy.device)
+            call("nemar_bias_grad", view(g, 0, 0, c), fptr(db), stream())
+        dx = torch.empty(shape, dtype=dtype, device=dy.device)
+        call("nemar_gather_taps", view(g), view(dx), k, c, sgn, stream())
+        return dx, db, None, None, None, None, None, None, None
+
+
 # ------------------------------------------------------------------------------------------------
 # InstanceNorm + activation (+ residual) with halo
 # ------------------------------------------------------------------------------------------------

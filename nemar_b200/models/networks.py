@@ -56,16 +56,46 @@ class Conv(nn.Module):
         return "%d->%d k%d s%d p%d%s" % (cin, cout, k, s, p, " transposed" if t else "")
 
     def run(self, x, x_pad=0, act=L.ACT_NONE, stats=False, out_f32=False, defer_bias_grad=False):
-        cin, cout, k, stride, pad, transposed, opt = self.meta
-        key = (x_pad, act, stats, out_f32, x.dtype, CONFIG.conv_engine, x.shape[3], defer_bias_grad)
-        cfg = self._cfgs.get(key)
-        if cfg is None:
+        return self._run(x, self.weight, self.bias, self.meta, "direct", x_pad, act, stats, out_f32, defer_bias_grad)
+
+    def _run(self, x, weight, bias, meta, tag, x_pad, act, stats, out_f32, defer_bias_grad):
+        cin, cout, k, stride, pad, transposed, opt = meta
+        key = (tag, x_pad, act, stats, out_f32, x.dtype, CONFIG.conv_engine, x.shape[3], defer_bias_grad)
+        ent = self._cfgs.get(key)
+        if ent is None:
             use_tc = tc_policy(cin, cout, k, stride, transposed, x.dtype, x.shape[3])
             cout_p = (cout + 15) // 16 * 16 if use_tc else cout
             cfg = F.ConvCfg(cin, cout, k, stride, pad, transposed, x_pad, act, stats, out_f32, opt, use_tc, cout_p,
-                            defer_bias_grad and self.bias is not None)
-            self._cfgs[key] = cfg
-        return F.Conv2dFn.apply(x, self.weight, self.bias, cfg, self._packed)
+                            defer_bias_grad and bias is not None)
+            ent = (cfg, self._packed if tag == "direct" else F.PackedWeights())
+            self._cfgs[key] = ent
+        return F.Conv2dFn.apply(x, weight, bias, ent[0], ent[1])
+
+    # ---- k x k convolutions with <= 4 input or output channels as 1x1 tensor-core convolutions ------------------
+    def taps_supported(self, x_dtype):
+        cin, cout, k, stride, pad, transposed, _ = self.meta
+        return (CONFIG.conv_engine == "auto" and x_dtype == torch.bfloat16 and not transposed and stride == 1 and k > 1 and
+                2 * pad == k - 1 and (cin <= 4 or cout <= 4))
+
+    def run_head_taps(self, x_padded, stats=True):
+        """cin <= 4: gather the k*k taps of the (halo'd) input into channels, then a 1x1 conv over k*k*cin channels.
+        -> (y, stats) like run(stats=True, defer_bias_grad=True)"""
+        cin, cout, k, _, pad, _, _ = self.meta
+        n, hp, wp, _ = x_padded.shape
+        kc = k * k * cin
+        u = F.GatherTapsFn.apply(x_padded, k, cin, 1, hp - 2 * pad, wp - 2 * pad, (kc + 31) // 32 * 32, x_padded.dtype)
+        w1 = self.weight.permute(0, 2, 3, 1).reshape(cout, kc, 1, 1)          # [co][(a,b,ci)]
+        return self._run(u, w1, self.bias, (kc, cout, 1, 1, 0, False, 0), "head_taps", 0, L.ACT_NONE, stats, False, True)
+
+    def run_tail_taps(self, x_padded, act, cp=4):
+        """cout <= 4: a 1x1 conv producing k*k*cout virtual channels on the halo'd grid, then the tap sum (+bias, act).
+        -> fp32 engine tensor [N,H,W,cp]"""
+        cin, cout, k, _, pad, _, _ = self.meta
+        n, hp, wp, _ = x_padded.shape
+        kc = k * k * cout
+        wv = self.weight.permute(2, 3, 0, 1).reshape(kc, cin, 1, 1)           # [(a,b,co)][ci]
+        v = self._run(x_padded, wv, None, (cin, kc, 1, 1, 0, False, 0), "tail_taps", 0, L.ACT_NONE, False, False, False)
+        return F.SumTapsFn.apply(v, self.bias, k, cout, -1, hp - 2 * pad, wp - 2 * pad, cp, act)
 
 
 def norm_act(x, stats, act, residual=None, res_pad=0, out_pad=0, pad_mode=L.PAD_REFLECT, bias=None):
@@ -135,8 +165,13 @@ class ResnetGenerator(nn.Module):
     def forward(self, x):
         m, nb = self.model, self.n_blocks
         g = lambda i: getattr(m, str(i))
-        t = F.ImagesToNHWC.apply(3, L.PAD_REFLECT, CONFIG.dtype, image_channels(self.input_nc), x)
-        t = conv_in_act(g(1), t, 3, L.ACT_RELU)
+        if g(1).taps_supported(CONFIG.dtype):
+            t = F.ImagesToNHWC.apply(3, L.PAD_REFLECT, CONFIG.dtype, self.input_nc, x)
+            y, st = g(1).run_head_taps(t)
+            t = norm_act(y, st, L.ACT_RELU, bias=g(1).bias)
+        else:
+            t = F.ImagesToNHWC.apply(3, L.PAD_REFLECT, CONFIG.dtype, image_channels(self.input_nc), x)
+            t = conv_in_act(g(1), t, 3, L.ACT_RELU)
         t = conv_in_act(g(4), t, 0, L.ACT_RELU)
         t = conv_in_act(g(7), t, 0, L.ACT_RELU, out_pad=1 if nb > 0 else 0)
         for i in range(nb):
@@ -144,7 +179,10 @@ class ResnetGenerator(nn.Module):
         b = 10 + nb
         t = conv_in_act(g(b), t, 0, L.ACT_RELU)
         t = conv_in_act(g(b + 3), t, 0, L.ACT_RELU, out_pad=3)
-        y = g(b + 7).run(t, x_pad=3, act=L.ACT_TANH, out_f32=True)
+        if g(b + 7).taps_supported(t.dtype):
+            y = g(b + 7).run_tail_taps(t, L.ACT_TANH)
+        else:
+            y = g(b + 7).run(t, x_pad=3, act=L.ACT_TANH, out_f32=True)
         return F.ToNCHW.apply(y, self.output_nc)
 
 

@@ -49,14 +49,15 @@ def test_unet_stn_forward_fp32_vs_oracle():
 # between the oracle evaluated in fp32 and in fp64 (Adam's first updates are ~lr*sign(g), and the LSGAN gradient
 # through InstanceNorm is a cancellation-dominated quantity: fp32-vs-fp64 oracle D_fake_TR differs by 7 % at step 2
 # and 21 % at step 3 on c1 — measured, see DESIGN.md "Parity").  They are therefore checked loosely.
-LATER_RTOL, LATER_ATOL = 0.35, 0.1
+L1_COLS, ADV_COLS = [0, 2, 4], [1, 3, 5, 6, 7]     # reconstruction / smoothness terms vs adversarial terms
 
 
 def _check_traj(losses, gold, first_rtol, first_atol):
     np.testing.assert_allclose(losses[0], gold[0], rtol=first_rtol, atol=first_atol, err_msg="step-1 losses %s" % NAMES)
     if len(losses) > 1:
-        np.testing.assert_allclose(losses[1:], gold[1:len(losses)], rtol=LATER_RTOL, atol=LATER_ATOL,
-                                   err_msg="later-step losses %s" % NAMES)
+        later, g = losses[1:], gold[1:len(losses)]
+        np.testing.assert_allclose(later[:, L1_COLS], g[:, L1_COLS], rtol=0.05, atol=0.5, err_msg="later-step L1/smoothness")
+        np.testing.assert_allclose(later[:, ADV_COLS], g[:, ADV_COLS], rtol=0.6, atol=0.3, err_msg="later-step adversarial terms")
 
 
 @pytest.mark.parametrize("name,steps", [("c1_affine64", 3), ("c4_multires256", 2)])

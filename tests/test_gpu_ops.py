@@ -376,3 +376,45 @@ def test_losses_linear_adam():
         ge[:1003] = g.to(DEV) * 2.0
         F.adam_step(pe, ge, m, v, 2e-4, 0.5, 0.999, 1e-8, s, 0.5)
     close(pe[:1003], pt.detach(), 1e-6, 1e-7, "adam")
+
+
+def test_tap_transforms_head_and_tail():
+    """k7 conv with 3 input (head) / 3 output (tail) channels == tap<->channel transform + 1x1 conv (fp32 check of
+    the two transform kernels against F.conv2d, using torch matmul for the 1x1 part)."""
+    n, h, w, k, p = 2, 12, 14, 7, 3
+    x = gen(n, 3, h, w, seed=1)
+    wt = gen(8, 3, k, k, seed=2, scale=0.1)
+    xr, wr = x.clone().requires_grad_(True), wt.clone().requires_grad_(True)
+    ref = TF.conv2d(TF.pad(xr, (p,) * 4, mode="reflect"), wr)
+    dg = gen(*ref.shape, seed=3)
+    (ref * dg).sum().backward()
+    xe = nhwc(x, torch.float32, p).requires_grad_(True)                       # [n,h+6,w+6,3]
+    u = F.GatherTapsFn.apply(xe, k, 3, 1, h, w, 160, torch.float32)
+    assert float(u[..., 147:].abs().max()) == 0.0
+    w1 = wt.permute(0, 2, 3, 1).reshape(8, 147).to(DEV)
+    y = u[..., :147] @ w1.t()
+    close(nchw(y), ref, 1e-4, 1e-4, "head via gather_taps")
+    (y * nhwc(dg, torch.float32)).sum().backward()
+    xz = torch.zeros(n, 3, h, w, requires_grad=True)
+    TF.pad(xz, (p,) * 4, mode="reflect").backward(nchw(xe.grad))
+    close(xz.grad, xr.grad, 1e-4, 1e-4, "head dgrad via sum_taps")
+    # tail: 8 -> 3 channels
+    x = gen(n, 8, h, w, seed=4)
+    wt = gen(3, 8, k, k, seed=5, scale=0.1)
+    b = gen(3, seed=6, scale=0.1)
+    xr, wr, br = x.clone().requires_grad_(True), wt.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    ref = torch.tanh(TF.conv2d(TF.pad(xr, (p,) * 4, mode="reflect"), wr, br))
+    dg = gen(*ref.shape, seed=7)
+    (ref * dg).sum().backward()
+    xe = nhwc(x, torch.float32, p).requires_grad_(True)                       # [n,h+6,w+6,8]
+    wv = wt.permute(2, 3, 0, 1).reshape(147, 8).to(DEV)
+    v = torch.zeros(n, h + 2 * p, w + 2 * p, 160, device=DEV)
+    v[..., :147] = xe @ wv.t()
+    be = b.to(DEV).requires_grad_(True)
+    y = F.SumTapsFn.apply(v, be, k, 3, -1, h, w, 4, L.ACT_TANH)
+    close(nchw(y)[:, :3], ref, 1e-4, 1e-4, "tail via sum_taps")
+    (y[..., :3] * nhwc(dg, torch.float32)).sum().backward()
+    xz = torch.zeros(n, 8, h, w, requires_grad=True)
+    TF.pad(xz, (p,) * 4, mode="reflect").backward(nchw(xe.grad))
+    close(xz.grad, xr.grad, 1e-4, 1e-4, "tail dgrad via gather_taps")
+    close(be.grad, br.grad, 1e-4, 1e-4, "tail bias grad")
