@@ -140,9 +140,11 @@ def test_gradients_vs_fp64_oracle(name, precision, engine):
             e_eng = float((p.grad.detach().double().cpu() - t).norm()) / nrm
             e_ref = float((yard[tag][i] - t).norm()) / nrm
             errs.append((e_eng, e_ref))
-            if e_eng > max(factor * e_ref, floor):
+            pure_noise = e_ref > 1.0 and e_eng < 2.5        # the reference arithmetic itself has lost this tensor entirely
+            if e_eng > max(factor * e_ref, floor) and not pure_noise:
                 bad.append((e_eng, e_ref, tag, k))
         summary[tag] = (float(np.median([a for a, _ in errs])), float(np.median([b for _, b in errs])))
+        assert summary[tag][0] <= factor * summary[tag][1] + floor, "median gradient error of net%s: %s" % (tag, summary[tag])
     print("median gradient error vs fp64 truth (engine, reference-arithmetic yardstick):", summary)
     msg = "\n".join("%s.%s engine err %.3e, yardstick err %.3e" % (t, k, a, b) for a, b, t, k in sorted(bad, reverse=True)[:30])
     assert not bad, "gradients less accurate than allowed (worst first):\n" + msg
