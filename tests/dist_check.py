@@ -1,0 +1,71 @@
+"""Launched by torchrun on N GPUs: N-rank data-parallel step == single-process step on the same global batch.
+Every rank runs optimize_parameters on its shard (one all-reduce per gradient bucket); rank 0 then repeats the step
+alone on the full global batch and compares the averaged gradient buckets."""
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from nemar_b200.engine import parallel  # noqa: E402
+from oracle import nemar_oracle as O  # noqa: E402
+from tests import helpers as H  # noqa: E402
+
+
+def grads_after_step(model, A, B):
+    cap = {}
+    for name, opt in (("TR", model.optimizer_TR), ("D", model.optimizer_D)):
+        inner = opt.grad_hook
+
+        def hook(flat, inner=inner, name=name):
+            scale = inner(flat)
+            cap[name] = (flat * scale).detach().clone()
+            return scale
+        opt.grad_hook = hook
+    model.set_input({"A": A, "B": B, "A_paths": "", "B_paths": ""})
+    model.optimize_parameters()
+    torch.cuda.synchronize()
+    return cap
+
+
+def main():
+    world, rank, local = parallel.init_process_group_from_env("nccl")
+    torch.cuda.set_device(local)
+    per = 2
+    kw, _, extra = H.CASE_FLAGS["c1_affine64"]
+    cfg = O.OracleConfig(**kw)
+    T, R, Ds = O.make_states(cfg, seed=11)
+    A, B = O.synthetic_batch(per * world, cfg.height, cfg.width, seed=1)
+
+    def build(batch):
+        from nemar_b200.models import create_model
+        opt = H.engine_opt(cfg, batch, extra, "fp32", "generic", gpu_ids=str(local), ckpt="/tmp/nemar_dist_%d" % rank)
+        m = create_model(opt)
+        H.load_states(m, T, R, Ds)
+        return m
+
+    dp = build(per)
+    g_dp = grads_after_step(dp, parallel.shard_batch(A, rank, world), parallel.shard_batch(B, rank, world))
+    calls = dp.allreduce.calls
+    ok = True
+    if rank == 0:
+        was = dist.is_initialized
+        single = build(per * world)
+        single.optimizer_TR.grad_hook = lambda flat: 1.0       # no exchange: the whole global batch is local
+        single.optimizer_D.grad_hook = lambda flat: 1.0
+        g_1 = grads_after_step(single, A, B)
+        for k in ("TR", "D"):
+            rel = float((g_dp[k] - g_1[k]).norm() / g_1[k].norm())
+            print("bucket %s: |dp - single| / |single| = %.3e   (all-reduce calls per step: %d)" % (k, rel, calls))
+            ok = ok and rel < 2e-2          # fp32 rounding amplified by the GAN gradient (see DESIGN.md "Parity")
+        print("DIST_CHECK", "OK" if ok else "FAILED", "world", world)
+    dist.barrier()
+    dist.destroy_process_group()
+    sys.exit(0 if ok else 1)
+
+
+if __name__ == "__main__":
+    main()
