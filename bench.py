@@ -151,7 +151,11 @@ def run_engine(args):
     global_batch = args.batch * world
     value = global_batch * args.steps / (ms / 1e3)
     e2e_value = global_batch * args.steps / (ms_e2e / 1e3)
+    if world > 1:
+        dist.barrier()
     if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
         return
     # ---- roofline of the dominant kernel (largest share of timed kernel time)
     roof = None
@@ -187,6 +191,7 @@ def run_engine(args):
     if args.grid_sample_bench:
         out["grid_sample"] = grid_sample_bench(dev, peaks)
     print(json.dumps(out))
+    sys.stdout.flush()
 
 
 def pick_cpu_threads():

@@ -352,15 +352,16 @@ plane_reduce_kernel(TView x, const float* __restrict__ stats, int act, TView dy,
   const int c = x.c, G = c / V;
   for (int k = threadIdx.x; k < 2 * c; k += blockDim.x) sacc[k] = 0.f;
   __syncthreads();
-  const int64_t hw = (int64_t)x.h * x.w;
-  const int64_t items = hw * G;
-  const int64_t per_block = (items + gridDim.x - 1) / gridDim.x;
+  // per-sample item counts fit 32 bits (<= 1030^2 * 64): 32-bit index arithmetic keeps the loop HBM-bound
+  const uint32_t hw = (uint32_t)x.h * (uint32_t)x.w;
+  const uint32_t items = hw * (uint32_t)G;
+  const uint32_t per_block = (items + gridDim.x - 1) / gridDim.x;
   // align each block's range to a multiple of G so that a thread keeps one channel group when
   // blockDim % G == 0 (register accumulation); otherwise fall back to per-item shared atomics.
-  const int64_t per_block_al = (per_block + G - 1) / G * G;
-  const int64_t lo = blockIdx.x * per_block_al;
-  int64_t hi = lo + per_block_al;
-  if (hi > items) hi = items;
+  const uint32_t per_block_al = (per_block + G - 1) / G * G;
+  const uint32_t lo = blockIdx.x * per_block_al;
+  uint32_t hi = lo + per_block_al;
+  if (hi > items || hi < lo) hi = items;
   const bool reg_path = (blockDim.x % G) == 0;
   float a0[V], a1[V];
 #pragma unroll
@@ -368,12 +369,13 @@ plane_reduce_kernel(TView x, const float* __restrict__ stats, int act, TView dy,
   int my_cg = threadIdx.x % G;
   float hmean[V], hrstd[V];
   if (MODE == 1 && reg_path) load_mean_rstd<V>(stats, nn, c, my_cg * V, inv_hw, hmean, hrstd);
+  const uint32_t uw = (uint32_t)x.w, uG = (uint32_t)G;
 #pragma unroll 2
-  for (int64_t j = lo + threadIdx.x; j < hi; j += blockDim.x) {
-    int cg = (int)(j % G);
-    int64_t p = j / G;
-    int xx = (int)(p % x.w);
-    int yy = (int)(p / x.w);
+  for (uint32_t j = lo + threadIdx.x; j < hi; j += blockDim.x) {
+    const uint32_t p = j / uG;
+    const int cg = reg_path ? my_cg : (int)(j - p * uG);
+    const int yy = (int)(p / uw);
+    const int xx = (int)(p - (uint32_t)yy * uw);
     float v[V];
     ldv<T, V>((const T*)x.ptr + x.pix(nn, yy, xx) + cg * V, v);
     float s0[V], s1[V];
@@ -530,16 +532,18 @@ norm_act_fwd_kernel(TView x, const float* __restrict__ stats, int act, TView res
   // is a multiple of the group count every thread keeps ONE channel group, so mean/rstd are computed once.
   const int nn = blockIdx.y;
   const int G = y.c / V;
-  const int64_t items = (int64_t)y.hp * y.wp * G;
-  const bool fixed = (blockDim.x % G) == 0 && ((int64_t)gridDim.x * blockDim.x) % G == 0;
+  const uint32_t items = (uint32_t)y.hp * (uint32_t)y.wp * (uint32_t)G;   // per sample: fits 32 bits
+  const bool fixed = (blockDim.x % G) == 0;
+  const int my_cg = (int)(threadIdx.x % G);
   float hmean[V], hrstd[V];
-  if (stats && fixed) load_mean_rstd<V>(stats, nn, y.c, (int)(threadIdx.x % G) * V, inv_hw, hmean, hrstd);
+  if (stats && fixed) load_mean_rstd<V>(stats, nn, y.c, my_cg * V, inv_hw, hmean, hrstd);
+  const uint32_t uG = (uint32_t)G, uwp = (uint32_t)y.wp, step = gridDim.x * blockDim.x;
 #pragma unroll 2
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < items; i += (int64_t)gridDim.x * blockDim.x) {
-    int cg = (int)(i % G);
-    int64_t r = i / G;
-    int xp = (int)(r % y.wp);
-    int yp = (int)(r / y.wp);
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < items; i += step) {
+    const uint32_t r = i / uG;
+    const int cg = fixed ? my_cg : (int)(i - r * uG);
+    const int yp = (int)(r / uwp);
+    const int xp = (int)(r - (uint32_t)yp * uwp);
     int ys = yp - y.pad, xs = xp - y.pad;
     bool halo = ys < 0 || ys >= y.h || xs < 0 || xs >= y.w;
     float v[V];
@@ -619,8 +623,8 @@ norm_act_bwd_apply_kernel(TView x, const float* __restrict__ stats, int act, TVi
   extern __shared__ float sdb[];   // [c] when db != nullptr
   const int nn = blockIdx.y;
   const int G = x.c / V;
-  const int64_t items = (int64_t)x.h * x.w * G;
-  const bool fixed = (blockDim.x % G) == 0 && ((int64_t)gridDim.x * blockDim.x) % G == 0;
+  const uint32_t items = (uint32_t)x.h * (uint32_t)x.w * (uint32_t)G;   // per sample: fits 32 bits
+  const bool fixed = (blockDim.x % G) == 0;
   const int my_cg = (int)(threadIdx.x % G);
   if (db) {
     for (int k = threadIdx.x; k < x.c; k += blockDim.x) sdb[k] = 0.f;
@@ -635,12 +639,13 @@ norm_act_bwd_apply_kernel(TView x, const float* __restrict__ stats, int act, TVi
 #pragma unroll
     for (int k = 0; k < V; ++k) { hm1[k] = __ldg(rd + 2 * k) * inv_hw; hm2[k] = __ldg(rd + 2 * k + 1) * inv_hw; }
   }
+  const uint32_t uG = (uint32_t)G, uw = (uint32_t)x.w, step = gridDim.x * blockDim.x;
 #pragma unroll 2
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < items; i += (int64_t)gridDim.x * blockDim.x) {
-    int cg = (int)(i % G);
-    int64_t r = i / G;
-    int xx = (int)(r % x.w);
-    int yy = (int)(r / x.w);
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < items; i += step) {
+    const uint32_t r = i / uG;
+    const int cg = fixed ? my_cg : (int)(i - r * uG);
+    const int yy = (int)(r / uw);
+    const int xx = (int)(r - (uint32_t)yy * uw);
     float g[V], v[V], o[V];
     load_fold<T, V>(dy, nn, yy, xx, cg * V, pad_mode, g);
     if (has_dres) {

@@ -111,7 +111,7 @@ class KernelTimer:
         self.records = []
 
     def enable(self, flag):
-        self.on = bool(flag)
+        self.on = int(flag)          # 1: conv launches (roofline), 2: every engine call (per-op breakdown)
         self.records = []
 
     def key_and_flops(self, name, args):
@@ -146,8 +146,11 @@ TIMER = KernelTimer()
 
 def call(name, *args):
     COUNTERS["launches"] += 1
-    if TIMER.on and name in KernelTimer.CONV:
-        key, geo, flops = TIMER.key_and_flops(name, args)
+    if TIMER.on and (name in KernelTimer.CONV or TIMER.on >= 2):
+        if name in KernelTimer.CONV:
+            key, geo, flops = TIMER.key_and_flops(name, args)
+        else:
+            key, geo, flops = name.replace("nemar_", ""), name, 0.0
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         _call(name, *args)
