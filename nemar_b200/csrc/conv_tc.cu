@@ -111,7 +111,23 @@ struct GatherParams {
   int cd;                        // destination channels
   const float* bias;
   int act;
+  float* stats;                  // optional [n][cd][2]: per-(sample, channel) sum / sum of squares of the fp32 pre-activation
 };
+
+// Sum each of a lane's 32 values across the 32 lanes of the warp with 31 shuffles: on return a[0] of lane L holds
+// the warp-wide total of original index L (recursive halving: at offset o a lane keeps the half selected by bit o).
+__device__ __forceinline__ void warp_transpose_sum(float (&a)[32], int lane) {
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) {
+    const bool upper = (lane & o) != 0;
+#pragma unroll
+    for (int i = 0; i < o; ++i) {
+      const float send = upper ? a[i] : a[i + o];
+      const float keep = upper ? a[i + o] : a[i];
+      a[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+    }
+  }
+}
 
 template <int BN, int BK>
 struct GatherCfg {
@@ -123,7 +139,7 @@ struct GatherCfg {
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : (STAGES_RAW < 2 ? 2 : STAGES_RAW);
   static constexpr uint32_t TX_BYTES = BM * BK * 2 + BN * BK * 2;
   static constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
-  static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + 1024 + 256;
+  static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + 1024 + 256 + (size_t)BN * 2 * sizeof(float);
 };
 
 template <int BN, int BK, bool F32OUT>
@@ -138,6 +154,7 @@ tc_gather_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full = empty_bar + STAGES;
   uint32_t* tmem_slot = (uint32_t*)(tmem_full + 1);
+  float* sstat = (float*)(tmem_slot + 2);          // [BN][2] partial InstanceNorm statistics of this tile
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   int t = blockIdx.x;
@@ -204,12 +221,34 @@ tc_gather_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const bool valid = px < P.dw && py < P.dh && pn < P.dn;
     const long long off = (long long)pn * P.ds_n + (long long)(py * P.ostep + P.oy0) * P.ds_y +
                           (long long)(px * P.ostep + P.ox0) * P.ds_x + c0;
+    const int et = threadIdx.x - 64;                       // 0..127 within the epilogue warps
+    if (P.stats) {
+      for (int k = et; k < 2 * BN; k += 128) sstat[k] = 0.f;
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+    }
     mbar_wait(tmem_full, 0);
     tc_fence_after();
 #pragma unroll 1
     for (int cc = 0; cc < (int)Cfg::TMEM_COLS; cc += 32) {
       float v[32];
       tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)cc, v);
+      if (P.stats) {
+        // InstanceNorm statistics in the epilogue: column sums of (acc + bias) and its square over this warp's 32
+        // pixels via a transposing butterfly, combined across the four epilogue warps in shared memory
+        float s1[32], s2[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int ch = c0 + cc + j;
+          float f = (valid && cc + j < BN && ch < P.cd) ? v[j] + (P.bias ? __ldg(P.bias + ch) : 0.f) : 0.f;
+          s1[j] = f; s2[j] = f * f;
+        }
+        warp_transpose_sum(s1, lane);
+        warp_transpose_sum(s2, lane);
+        if (cc + lane < BN) {
+          atomicAdd(&sstat[(cc + lane) * 2], s1[0]);
+          atomicAdd(&sstat[(cc + lane) * 2 + 1], s2[0]);
+        }
+      }
       if (valid) {
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
@@ -234,6 +273,13 @@ tc_gather_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
         }
       }
+    }
+    if (P.stats) {
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      // the tile lies inside one sample (host guarantees tn == 1): one global RED per (channel, statistic)
+      float* gs = P.stats + ((long long)n0 * P.cd + c0) * 2;
+      for (int k = et; k < 2 * BN; k += 128)
+        if (c0 + (k >> 1) < P.cd) atomicAdd(gs + k, sstat[k]);
     }
     tc_fence_before();
   }
@@ -321,6 +367,8 @@ int tc_gather_gemm(const nemar_tensor* src_in, const nemar_tensor* dst_in, const
   if (rc) return rc;
 
   const int nclass = (gg.sd == 2) ? 4 : 1;
+  bool fused_stats = stats != nullptr;
+  if (stats) NEMAR_REQUIRE(act == NEMAR_ACT_NONE, "tc_gather_gemm: statistics need the pre-activation output");
   for (int cls = 0; cls < nclass; ++cls) {
     GatherParams P;
     const int pyc = cls >> 1, pxc = cls & 1;   // destination parity of this class (sd == 2)
@@ -356,6 +404,10 @@ int tc_gather_gemm(const nemar_tensor* src_in, const nemar_tensor* dst_in, const
     P.cd = dst.c;
     P.bias = bias;
     P.act = act;
+    // statistics are fused when every tile lies inside one sample; tiny maps (several samples per tile) use the
+    // separate reduction pass below
+    P.stats = (stats && P.tn == 1 && !f32) ? stats : nullptr;
+    if (stats && !P.stats) fused_stats = false;
     CUtensorMap tmA;
     rc = make_act_map(&tmA, &src, BK, P.tw, P.th, P.tn, gg.sm);
     if (rc) return rc;
@@ -369,8 +421,9 @@ int tc_gather_gemm(const nemar_tensor* src_in, const nemar_tensor* dst_in, const
     }
     if (rc) return rc;
   }
-  if (stats) {
-    NEMAR_REQUIRE(act == NEMAR_ACT_NONE, "tc_gather_gemm: statistics need the pre-activation output");
+  if (stats && !fused_stats) {
+    // (mixed fused / unfused classes cannot occur: tn depends only on the class extents, which differ by <= 1)
+    cudaMemsetAsync(stats, 0, sizeof(float) * 2 * (size_t)dst.n * dst.c, s);
     return nemar_instnorm_stats(dst_in, stats, (void*)s);
   }
   return 0;

@@ -14,7 +14,9 @@ template <typename T, int V>
 __device__ __forceinline__ void load_fold(const TView& d, int nn, int y, int x, int c0, int pad_mode,
                                           float (&g)[V]) {
   const T* base = (const T*)d.ptr;
-  if (d.pad == 0 || pad_mode != NEMAR_PAD_REFLECT) {
+  // fast path: no halo, or a pixel whose mirror images do not exist (more than `pad` away from every border)
+  if (d.pad == 0 || pad_mode != NEMAR_PAD_REFLECT ||
+      (y > d.pad && y < d.h - 1 - d.pad && x > d.pad && x < d.w - 1 - d.pad)) {
     ldv<T, V>(base + d.pix(nn, y, x) + c0, g);
     return;
   }
@@ -203,17 +205,19 @@ NEMAR_API int nemar_cast_view(const nemar_tensor* src, const nemar_tensor* dst, 
 }
 
 // ---- tap <-> channel transforms (k7 head / tail as 1x1 tensor-core convolutions) ----------------
-__global__ void gather_taps_kernel(TView s, TView d, int k, int c, int sgn) {
+template <int KK, int CC>
+__global__ void gather_taps_kernel(TView s, TView d, int k_rt, int c_rt, int sgn) {
+  const int k = KK > 0 ? KK : k_rt, c = CC > 0 ? CC : c_rt;
   // one thread -> 8 consecutive destination channels of one pixel (one 16-byte store when d is bf16)
-  const int groups = d.c / 8;
+  const uint32_t groups = d.c / 8;
   const int kc = k * k * c;
-  const int64_t total = (int64_t)d.n * d.h * d.w * groups;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    int g = (int)(i % groups);
-    int64_t r = i / groups;
-    int x = (int)(r % d.w); r /= d.w;
-    int y = (int)(r % d.h);
-    int nn = (int)(r / d.h);
+  const uint32_t total = (uint32_t)d.n * d.h * d.w * groups;      // < 2^32 for every size on the path
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    uint32_t r = i / groups;
+    const int g = (int)(i - r * groups);
+    const int x = (int)(r % (uint32_t)d.w); r /= (uint32_t)d.w;
+    const int y = (int)(r % (uint32_t)d.h);
+    const int nn = (int)(r / (uint32_t)d.h);
     float v[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -241,7 +245,9 @@ __global__ void gather_taps_kernel(TView s, TView d, int k, int c, int sgn) {
   }
 }
 
-__global__ void sum_taps_kernel(TView s, TView d, int k, int c, int sgn, const float* __restrict__ bias, int act) {
+template <int KK, int CC>
+__global__ void sum_taps_kernel(TView s, TView d, int k_rt, int c_rt, int sgn, const float* __restrict__ bias, int act) {
+  const int k = KK > 0 ? KK : k_rt, c = CC > 0 ? CC : c_rt;
   const int64_t total = (int64_t)d.n * d.h * d.w;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     int x = (int)(i % d.w);
@@ -275,7 +281,8 @@ NEMAR_API int nemar_gather_taps(const nemar_tensor* src, const nemar_tensor* dst
                 "gather_taps: bad arguments");
   TView s = make_view(src), d = make_view(dst);
   int64_t total = (int64_t)d.n * d.h * d.w * (d.c / 8);
-  gather_taps_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(s, d, k, c, sgn);
+  if (k == 7 && c == 3) gather_taps_kernel<7, 3><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(s, d, k, c, sgn);
+  else gather_taps_kernel<0, 0><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(s, d, k, c, sgn);
   NEMAR_LAUNCH_CHECK();
   return 0;
 }
@@ -286,7 +293,8 @@ NEMAR_API int nemar_sum_taps(const nemar_tensor* src, const nemar_tensor* dst, i
   NEMAR_REQUIRE(k > 0 && c > 0 && c <= 4 && c <= dst->c && src->c >= k * k * c && (sgn == 1 || sgn == -1), "sum_taps: bad arguments");
   TView s = make_view(src), d = make_view(dst);
   int64_t total = (int64_t)d.n * d.h * d.w;
-  sum_taps_kernel<<<grid_for(total, 128), 128, 0, (cudaStream_t)stream>>>(s, d, k, c, sgn, bias, act);
+  if (k == 7 && c == 3) sum_taps_kernel<7, 3><<<grid_for(total, 128), 128, 0, (cudaStream_t)stream>>>(s, d, k, c, sgn, bias, act);
+  else sum_taps_kernel<0, 0><<<grid_for(total, 128), 128, 0, (cudaStream_t)stream>>>(s, d, k, c, sgn, bias, act);
   NEMAR_LAUNCH_CHECK();
   return 0;
 }
@@ -435,8 +443,8 @@ static int launch_plane_reduce(const nemar_tensor* xt, const float* stats, int a
     bool vec = view_vec_ok<T>(xt) && (!dyt || view_vec_ok<T>(dyt));
     int G = vec ? x.c / VV : x.c;
     int64_t items = hw * G;
-    int chunks = (int)((items + 256 * 16 - 1) / (256 * 16));
-    int cap = (148 * 8 + x.n - 1) / x.n;
+    int chunks = (int)((items + 256 * 4 - 1) / (256 * 4));      // >= 4 items per thread, enough blocks to fill 148 SMs
+    int cap = (148 * 16 + x.n - 1) / x.n;
     if (chunks > cap) chunks = cap;
     if (chunks < 1) chunks = 1;
     size_t smem = sizeof(float) * 2 * x.c;
