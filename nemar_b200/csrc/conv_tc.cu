@@ -112,6 +112,7 @@ struct GatherParams {
   const float* bias;
   int act;
   float* stats;                  // optional [n][cd][2]: per-(sample, channel) sum / sum of squares of the fp32 pre-activation
+  int kstagger;                  // 1: rotate each CTA's K-loop start
 };
 
 // Sum each of a lane's 32 values across the 32 lanes of the warp with 31 shuffles: on return a[0] of lane L holds
@@ -182,8 +183,12 @@ tc_gather_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (lane == 0) {
       // ===== TMA producer =====
       int stage = 0; uint32_t phase = 0;
+      // every CTA walks the K loop from a different starting step (the accumulation order is irrelevant): CTAs
+      // running concurrently then fetch DIFFERENT weight tiles instead of hammering the same L2 lines
+      int kk = P.kstagger ? (int)((blockIdx.x * 5u + blockIdx.y * 3u) % (unsigned)ksteps) : 0;
       for (int ks = 0; ks < ksteps; ++ks) {
-        const int tap = ks / P.kchunks, kc = ks - tap * P.kchunks;
+        const int tap = kk / P.kchunks, kc = kk - tap * P.kchunks;
+        if (++kk == ksteps) kk = 0;
         mbar_wait(&empty_bar[stage], phase ^ 1);
         uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
         mbar_expect_tx(&full_bar[stage], Cfg::TX_BYTES);
@@ -404,9 +409,14 @@ int tc_gather_gemm(const nemar_tensor* src_in, const nemar_tensor* dst_in, const
     P.cd = dst.c;
     P.bias = bias;
     P.act = act;
+    static const int stag = [] { const char* e = getenv("NEMAR_TC_STAGGER"); return e ? atoi(e) : 1; }();
+    P.kstagger = stag;
     // statistics are fused when every tile lies inside one sample; tiny maps (several samples per tile) use the
     // separate reduction pass below
-    P.stats = (stats && P.tn == 1 && !f32) ? stats : nullptr;
+    static const int fuse = [] { const char* e = getenv("NEMAR_FUSED_STATS"); return e ? atoi(e) : 0; }();
+    // (measured on B200: the butterfly + REDs lengthen the epilogue by more than the separate L2-resident
+    //  reduction pass costs, so the fused variant is opt-in: NEMAR_FUSED_STATS=1)
+    P.stats = (fuse && stats && P.tn == 1 && !f32) ? stats : nullptr;
     if (stats && !P.stats) fused_stats = false;
     CUtensorMap tmA;
     rc = make_act_map(&tmA, &src, BK, P.tw, P.th, P.tn, gg.sm);

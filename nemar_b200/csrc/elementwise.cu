@@ -443,8 +443,8 @@ static int launch_plane_reduce(const nemar_tensor* xt, const float* stats, int a
     bool vec = view_vec_ok<T>(xt) && (!dyt || view_vec_ok<T>(dyt));
     int G = vec ? x.c / VV : x.c;
     int64_t items = hw * G;
-    int chunks = (int)((items + 256 * 4 - 1) / (256 * 4));      // >= 4 items per thread, enough blocks to fill 148 SMs
-    int cap = (148 * 16 + x.n - 1) / x.n;
+    int chunks = (int)((items + 256 * 16 - 1) / (256 * 16));    // more blocks were measured slower (2C global REDs per block)
+    int cap = (148 * 8 + x.n - 1) / x.n;
     if (chunks > cap) chunks = cap;
     if (chunks < 1) chunks = 1;
     size_t smem = sizeof(float) * 2 * x.c;
