@@ -282,29 +282,30 @@ def grid_sample_bench(dev, peaks, size=1024, n=4, iters=20):
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     px = n * size * size
     res = {}
+    # every buffer is allocated up front and the kernels are launched through the C ABI directly, right behind the
+    # L2-flush memset, so that no host-side launch latency sits inside the event pair
+    out = torch.empty_like(img)
+    dimg = torch.zeros_like(img)
+    dgrid = torch.empty_like(grid)
     for name in ("fwd", "bwd"):
         times = []
         for it in range(iters + 3):
+            if name == "bwd":
+                dimg.zero_()
             flush.zero_()
-            gr = grid.clone().requires_grad_(name == "bwd")
-            im = img.clone().requires_grad_(name == "bwd")
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
             if name == "fwd":
-                e0.record()
-                F.GridSampleFn.apply(gr, im, None)
-                e1.record()
+                F.call("nemar_grid_sample_fwd", F.fptr(img), None, 1, n, 3, size, size, F.fptr(grid), size, size,
+                       F.fptr(out), None, None, F.stream())
             else:
-                out = F.GridSampleFn.apply(gr, im, None)
-                dimg = torch.zeros_like(im)
-                dgrid = torch.empty_like(grid)
-                e0.record()
                 F.call("nemar_grid_sample_bwd", F.fptr(img), None, 1, n, 3, size, size, F.fptr(grid), size, size,
                        F.fptr(dout), None, F.fptr(dimg), None, F.fptr(dgrid), F.stream())
-                e1.record()
+            e1.record()
             torch.cuda.synchronize()
             if it >= 3:
                 times.append(e0.elapsed_time(e1))
-        ms = sum(times) / len(times)
+        ms = sorted(times)[len(times) // 2]
         bpp = 32 if name == "fwd" else 52
         gbs = px * bpp / (ms / 1e3) / 1e9
         res[name] = {"gbs": round(gbs, 1), "frac_of_hbm_peak": round(gbs / peaks["hbm"], 4), "ms": round(ms, 4),
