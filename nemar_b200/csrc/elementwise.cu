@@ -443,9 +443,9 @@ static int launch_plane_reduce(const nemar_tensor* xt, const float* stats, int a
     bool vec = view_vec_ok<T>(xt) && (!dyt || view_vec_ok<T>(dyt));
     int G = vec ? x.c / VV : x.c;
     int64_t items = hw * G;
-    // latency-bound (ncu: 12-22 % warps active, long-scoreboard stalls): ~8 blocks of 256 threads per SM over
-    // the whole launch, at least 4 items per thread; many more blocks were measured slower (2C global REDs each)
-    int chunks = (int)((items + 256 * 4 - 1) / (256 * 4));
+    // measured: more (smaller) blocks are SLOWER — every block ends with 2C global REDs onto the same [n][c] cells,
+    // and that serialised tail, not the streaming loop, is what grows with the block count
+    int chunks = (int)((items + 256 * 16 - 1) / (256 * 16));
     int cap = (148 * 8 + x.n - 1) / x.n;
     if (chunks > cap) chunks = cap;
     if (chunks < 1) chunks = 1;
@@ -592,7 +592,7 @@ norm_act_fwd_kernel(TView x, const float* __restrict__ stats, int act, TView res
 }
 
 static int plane_chunks(int64_t items_per_sample, int n) {
-  int64_t chunks = (items_per_sample + 256 * 4 - 1) / (256 * 4);
+  int64_t chunks = (items_per_sample + 256 * 8 - 1) / (256 * 8);
   int64_t cap = (148 * 16 + n - 1) / n;
   if (chunks > cap) chunks = cap;
   if (chunks < 1) chunks = 1;
