@@ -352,21 +352,13 @@ NEMAR_API int nemar_copy_view_bwd(const nemar_tensor* dsrc_out, const nemar_tens
 // MODE 0: (sum x, sum x^2)             MODE 1: (sum g, sum g*xhat), g = fold(dy)*act'(pre)
 // grid = (chunks, n); partial sums are combined in shared memory then one global atomic per (c, stat).
 template <typename T, int V, int MODE>
-__global__ void __launch_bounds__(256, 3)
+__global__ void __launch_bounds__(256)
 plane_reduce_kernel(TView x, const float* __restrict__ stats, int act, TView dy, int pad_mode,
                     float inv_hw, float* __restrict__ out) {
-  extern __shared__ float sacc[];  // [c][2] accumulators, then [c][2] (mean, rstd) for MODE 1
+  extern __shared__ float sacc[];  // [c][2]
   const int nn = blockIdx.y;
   const int c = x.c, G = c / V;
-  float* smr = sacc + 2 * c;
   for (int k = threadIdx.x; k < 2 * c; k += blockDim.x) sacc[k] = 0.f;
-  if (MODE == 1) {
-    for (int k = threadIdx.x; k < c; k += blockDim.x) {
-      float m[1], r[1];
-      load_mean_rstd<1>(stats, nn, c, k, inv_hw, m, r);
-      smr[2 * k] = m[0]; smr[2 * k + 1] = r[0];
-    }
-  }
   __syncthreads();
   // per-sample item counts fit 32 bits (<= 1030^2 * 64): 32-bit index arithmetic keeps the loop HBM-bound
   const uint32_t hw = (uint32_t)x.h * (uint32_t)x.w;
@@ -383,8 +375,10 @@ plane_reduce_kernel(TView x, const float* __restrict__ stats, int act, TView dy,
 #pragma unroll
   for (int k = 0; k < V; ++k) { a0[k] = 0.f; a1[k] = 0.f; }
   int my_cg = threadIdx.x % G;
+  float hmean[V], hrstd[V];
+  if (MODE == 1 && reg_path) load_mean_rstd<V>(stats, nn, c, my_cg * V, inv_hw, hmean, hrstd);
   const uint32_t uw = (uint32_t)x.w, uG = (uint32_t)G;
-#pragma unroll 4
+#pragma unroll 2
   for (uint32_t j = lo + threadIdx.x; j < hi; j += blockDim.x) {
     const uint32_t p = j / uG;
     const int cg = reg_path ? my_cg : (int)(j - p * uG);
@@ -399,10 +393,16 @@ plane_reduce_kernel(TView x, const float* __restrict__ stats, int act, TView dy,
     } else {
       float g[V];
       load_fold<T, V>(dy, nn, yy, xx, cg * V, pad_mode, g);
+      float mean[V], rstd[V];
+      if (reg_path) {
+#pragma unroll
+        for (int k = 0; k < V; ++k) { mean[k] = hmean[k]; rstd[k] = hrstd[k]; }
+      } else {
+        load_mean_rstd<V>(stats, nn, c, cg * V, inv_hw, mean, rstd);
+      }
 #pragma unroll
       for (int k = 0; k < V; ++k) {
-        const float2 mr = *reinterpret_cast<const float2*>(&smr[2 * (cg * V + k)]);
-        float xh = (v[k] - mr.x) * mr.y;
+        float xh = (v[k] - mean[k]) * rstd[k];
         float gg = g[k] * act_grad_from_x(xh, act);
         s0[k] = gg;
         s1[k] = gg * xh;
@@ -443,13 +443,11 @@ static int launch_plane_reduce(const nemar_tensor* xt, const float* stats, int a
     bool vec = view_vec_ok<T>(xt) && (!dyt || view_vec_ok<T>(dyt));
     int G = vec ? x.c / VV : x.c;
     int64_t items = hw * G;
-    // measured: more (smaller) blocks are SLOWER — every block ends with 2C global REDs onto the same [n][c] cells,
-    // and that serialised tail, not the streaming loop, is what grows with the block count
-    int chunks = (int)((items + 256 * 16 - 1) / (256 * 16));
+    int chunks = (int)((items + 256 * 16 - 1) / (256 * 16));    // more blocks were measured slower (2C global REDs per block)
     int cap = (148 * 8 + x.n - 1) / x.n;
     if (chunks > cap) chunks = cap;
     if (chunks < 1) chunks = 1;
-    size_t smem = sizeof(float) * (MODE == 1 ? 4 : 2) * x.c;
+    size_t smem = sizeof(float) * 2 * x.c;
     if (vec)
       plane_reduce_kernel<T, VV, MODE><<<dim3(chunks, x.n), 256, smem, s>>>(x, stats, act, dy, pad_mode,
                                                                             inv_hw, out);
@@ -545,15 +543,8 @@ norm_act_fwd_kernel(TView x, const float* __restrict__ stats, int act, TView res
   const uint32_t items = (uint32_t)y.hp * (uint32_t)y.wp * (uint32_t)G;   // per sample: fits 32 bits
   const bool fixed = (blockDim.x % G) == 0;
   const int my_cg = (int)(threadIdx.x % G);
-  extern __shared__ float smr[];     // [c][2] (mean, rstd) of this sample, computed once per block
-  if (stats) {
-    for (int k = threadIdx.x; k < y.c; k += blockDim.x) {
-      float m[1], r[1];
-      load_mean_rstd<1>(stats, nn, y.c, k, inv_hw, m, r);
-      smr[2 * k] = m[0]; smr[2 * k + 1] = r[0];
-    }
-    __syncthreads();
-  }
+  float hmean[V], hrstd[V];
+  if (stats && fixed) load_mean_rstd<V>(stats, nn, y.c, my_cg * V, inv_hw, hmean, hrstd);
   const uint32_t uG = (uint32_t)G, uwp = (uint32_t)y.wp, step = gridDim.x * blockDim.x;
 #pragma unroll 2
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < items; i += step) {
@@ -572,11 +563,15 @@ norm_act_fwd_kernel(TView x, const float* __restrict__ stats, int act, TView res
       xs = reflect_idx(xs, y.w);
       ldv<T, V>((const T*)x.ptr + x.pix(nn, ys, xs) + cg * V, v);
       if (stats) {
+        float mean[V], rstd[V];
+        if (fixed) {
 #pragma unroll
-        for (int k = 0; k < V; ++k) {
-          const float2 mr = *reinterpret_cast<const float2*>(&smr[2 * (cg * V + k)]);
-          v[k] = (v[k] - mr.x) * mr.y;
+          for (int k = 0; k < V; ++k) { mean[k] = hmean[k]; rstd[k] = hrstd[k]; }
+        } else {
+          load_mean_rstd<V>(stats, nn, y.c, cg * V, inv_hw, mean, rstd);
         }
+#pragma unroll
+        for (int k = 0; k < V; ++k) v[k] = (v[k] - mean[k]) * rstd[k];
       }
 #pragma unroll
       for (int k = 0; k < V; ++k) v[k] = act_fwd(v[k], act);
@@ -614,11 +609,11 @@ NEMAR_API int nemar_norm_act_fwd(const nemar_tensor* x, const float* stats, int 
     bool vec = view_vec_ok<T>(x) && view_vec_ok<T>(y) && (!residual || view_vec_ok<T>(residual));
     if (vec) {
       int64_t items = (int64_t)yv.hp * yv.wp * (yv.c / VV);
-      norm_act_fwd_kernel<T, VV><<<dim3(plane_chunks(items, yv.n), yv.n), 256, sizeof(float) * 2 * yv.c, s>>>(xv, stats, act, rv, residual != nullptr,
+      norm_act_fwd_kernel<T, VV><<<dim3(plane_chunks(items, yv.n), yv.n), 256, 0, s>>>(xv, stats, act, rv, residual != nullptr,
                                                                                           yv, pad_mode, inv_hw);
     } else {
       int64_t items = (int64_t)yv.hp * yv.wp * yv.c;
-      norm_act_fwd_kernel<T, 1><<<dim3(plane_chunks(items, yv.n), yv.n), 256, sizeof(float) * 2 * yv.c, s>>>(xv, stats, act, rv, residual != nullptr,
+      norm_act_fwd_kernel<T, 1><<<dim3(plane_chunks(items, yv.n), yv.n), 256, 0, s>>>(xv, stats, act, rv, residual != nullptr,
                                                                                          yv, pad_mode, inv_hw);
     }
   });
@@ -627,32 +622,31 @@ NEMAR_API int nemar_norm_act_fwd(const nemar_tensor* x, const float* stats, int 
 }
 
 template <typename T, int V>
-__global__ void __launch_bounds__(256, 3)
+__global__ void __launch_bounds__(256)
 norm_act_bwd_apply_kernel(TView x, const float* __restrict__ stats, int act, TView dy, int pad_mode,
                           const float* __restrict__ red, TView dx, TView dres, int has_dres,
                           int dres_acc, float inv_hw, float* __restrict__ db) {
   // grid = (chunks, n); thread keeps one channel group when blockDim % G == 0 (statistics hoisted, bias-gradient
   // column sums kept in registers and flushed with one shared + one global atomic per channel per block).
-  extern __shared__ float sdb[];   // [c] bias-gradient partials, then [c][4] (mean, rstd, mean g, mean g*xhat)
+  extern __shared__ float sdb[];   // [c] when db != nullptr
   const int nn = blockIdx.y;
   const int G = x.c / V;
   const uint32_t items = (uint32_t)x.h * (uint32_t)x.w * (uint32_t)G;   // per sample: fits 32 bits
   const bool fixed = (blockDim.x % G) == 0;
   const int my_cg = (int)(threadIdx.x % G);
-  float4* sp = reinterpret_cast<float4*>(sdb + ((x.c + 3) & ~3));   // 16-byte aligned
-  for (int k = threadIdx.x; k < x.c; k += blockDim.x) {
-    sdb[k] = 0.f;
-    if (stats) {
-      float m[1], r[1];
-      load_mean_rstd<1>(stats, nn, x.c, k, inv_hw, m, r);
-      const float* rd = red + ((int64_t)nn * x.c + k) * 2;
-      sp[k] = make_float4(m[0], r[0], __ldg(rd) * inv_hw, __ldg(rd + 1) * inv_hw);
-    }
+  if (db) {
+    for (int k = threadIdx.x; k < x.c; k += blockDim.x) sdb[k] = 0.f;
+    __syncthreads();
   }
-  __syncthreads();
-  float bsum[V];
+  float hmean[V], hrstd[V], hm1[V], hm2[V], bsum[V];
 #pragma unroll
   for (int k = 0; k < V; ++k) bsum[k] = 0.f;
+  if (stats && fixed) {
+    load_mean_rstd<V>(stats, nn, x.c, my_cg * V, inv_hw, hmean, hrstd);
+    const float* rd = red + ((int64_t)nn * x.c + my_cg * V) * 2;
+#pragma unroll
+    for (int k = 0; k < V; ++k) { hm1[k] = __ldg(rd + 2 * k) * inv_hw; hm2[k] = __ldg(rd + 2 * k + 1) * inv_hw; }
+  }
   const uint32_t uG = (uint32_t)G, uw = (uint32_t)x.w, step = gridDim.x * blockDim.x;
 #pragma unroll 2
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < items; i += step) {
@@ -677,12 +671,21 @@ norm_act_bwd_apply_kernel(TView x, const float* __restrict__ stats, int act, TVi
     }
     ldv<T, V>((const T*)x.ptr + x.pix(nn, yy, xx) + cg * V, v);
     if (stats) {
+      float mean[V], rstd[V], m1[V], m2[V];
+      if (fixed) {
+#pragma unroll
+        for (int k = 0; k < V; ++k) { mean[k] = hmean[k]; rstd[k] = hrstd[k]; m1[k] = hm1[k]; m2[k] = hm2[k]; }
+      } else {
+        load_mean_rstd<V>(stats, nn, x.c, cg * V, inv_hw, mean, rstd);
+        const float* rd = red + ((int64_t)nn * x.c + cg * V) * 2;
+#pragma unroll
+        for (int k = 0; k < V; ++k) { m1[k] = __ldg(rd + 2 * k) * inv_hw; m2[k] = __ldg(rd + 2 * k + 1) * inv_hw; }
+      }
 #pragma unroll
       for (int k = 0; k < V; ++k) {
-        const float4 q = sp[cg * V + k];        // (mean, rstd, mean g, mean g*xhat)
-        float xh = (v[k] - q.x) * q.y;
+        float xh = (v[k] - mean[k]) * rstd[k];
         float gg = g[k] * act_grad_from_x(xh, act);
-        o[k] = q.y * (gg - q.z - xh * q.w);
+        o[k] = rstd[k] * (gg - m1[k] - xh * m2[k]);
       }
     } else {
 #pragma unroll
@@ -725,7 +728,7 @@ NEMAR_API int nemar_norm_act_bwd_apply(const nemar_tensor* x, const float* stats
   DISPATCH_DTYPE(xv.dtype, T, {
     constexpr int VV = VecTraits<T>::V;
     bool vec = view_vec_ok<T>(x) && view_vec_ok<T>(dy) && view_vec_ok<T>(dx) && (!dres || view_vec_ok<T>(dres));
-    size_t smem = sizeof(float) * (5 * xv.c + 8);
+    size_t smem = db ? sizeof(float) * xv.c : 0;
     if (db) cudaMemsetAsync(db, 0, sizeof(float) * xv.c, s);
     if (vec) {
       int64_t items = (int64_t)xv.h * xv.w * (xv.c / VV);

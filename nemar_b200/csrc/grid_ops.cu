@@ -6,6 +6,7 @@
 // models/stn/stn_losses.py:4-30.  grid_sample arithmetic follows ATen/native/GridSampler.h:26-36,205-207
 // (unnormalise ((g+1)*size-1)/2, floor taps, zeros padding, align_corners=False).
 #include "common.cuh"
+#include <cstdlib>
 
 // ---------------------------------------------------------------------------------------------
 // affine grid
@@ -235,6 +236,64 @@ grid_sample_fwd_kernel(const float* __restrict__ img0, const float* __restrict__
   }
 }
 
+// One output point per lane: for a smooth field the east taps of lane L are the west taps of lane L+1, so each lane
+// fetches only its west column (nw, sw) and receives the east column (ne, se) from its right neighbour by shuffle
+// (falling back to its own loads when the neighbour samples elsewhere).  Gathers of a warp are then contiguous
+// (one or two L1 wavefronts per request instead of four) and half as many.
+__global__ void __launch_bounds__(256)
+grid_sample_fwd_shared_kernel(const float* __restrict__ img0, const float* __restrict__ img1, int nimg, int n, int c,
+                              int h, int w, const float* __restrict__ grid, int ho, int wo, float* __restrict__ out0,
+                              float* __restrict__ out1, int32_t* __restrict__ idx) {
+  const int64_t ihw = (int64_t)h * w, ohw = (int64_t)ho * wo;
+  const int64_t total = (int64_t)n * ohw;
+  const int64_t total_r = (total + 31) / 32 * 32;
+  const int lane = threadIdx.x & 31;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total_r; i += (int64_t)gridDim.x * blockDim.x) {
+    const bool active = i < total;
+    const int64_t ii = active ? i : total - 1;
+    const int64_t opix = ii % ohw;
+    const int nn = (int)(ii / ohw);
+    const float2 g = __ldg(reinterpret_cast<const float2*>(grid) + ii);
+    const Taps t = make_taps(g.x, g.y, w, h);
+    if (idx && active) { idx[ii * 2] = t.x0; idx[ii * 2 + 1] = t.y0; }
+    const int x0 = t.x0, y0 = t.y0;
+    const bool xin0 = (x0 >= 0) & (x0 < w), xin1 = (x0 + 1 >= 0) & (x0 + 1 < w);
+    const bool yin0 = (y0 >= 0) & (y0 < h), yin1 = (y0 + 1 >= 0) & (y0 + 1 < h);
+    // can I take my east column from the next lane's west column?
+    const int nx0 = __shfl_down_sync(0xffffffffu, x0, 1);
+    const int ny0 = __shfl_down_sync(0xffffffffu, y0, 1);
+    const int nnn = __shfl_down_sync(0xffffffffu, nn, 1);
+    const bool borrow = lane < 31 && nnn == nn && ny0 == y0 && nx0 == x0 + 1;
+    for (int im = 0; im < nimg; ++im) {
+      const float* img = (im == 0 ? img0 : img1) + (int64_t)nn * c * ihw;
+      float* out = (im == 0 ? out0 : out1) + (int64_t)nn * c * ohw + opix;
+      for (int ch = 0; ch < c; ++ch) {
+        const float* pl = img + ch * ihw;
+        float vnw = 0.f, vsw = 0.f;
+        if (xin0) {
+          if (yin0) vnw = __ldg(pl + (int64_t)y0 * w + x0);
+          if (yin1) vsw = __ldg(pl + (int64_t)(y0 + 1) * w + x0);
+        }
+        float vne = __shfl_down_sync(0xffffffffu, vnw, 1);
+        float vse = __shfl_down_sync(0xffffffffu, vsw, 1);
+        if (!borrow) {
+          vne = 0.f; vse = 0.f;
+          if (xin1) {
+            if (yin0) vne = __ldg(pl + (int64_t)y0 * w + x0 + 1);
+            if (yin1) vse = __ldg(pl + (int64_t)(y0 + 1) * w + x0 + 1);
+          }
+        }
+        // same accumulation order as ATen's kernel: nw, ne, sw, se (out-of-range taps hold 0 and add exactly 0)
+        float acc = vnw * t.nw;
+        acc += vne * t.ne;
+        acc += vsw * t.sw;
+        acc += vse * t.se;
+        if (active) out[ch * ohw] = acc;
+      }
+    }
+  }
+}
+
 NEMAR_API int nemar_grid_sample_fwd(const float* img0, const float* img1, int nimg, int n, int c, int h,
                                     int w, const float* grid, int ho, int wo, float* out0, float* out1,
                                     int32_t* idx_dump, void* stream) {
@@ -243,7 +302,12 @@ NEMAR_API int nemar_grid_sample_fwd(const float* img0, const float* img1, int ni
   NEMAR_REQUIRE(n > 0 && c > 0 && h > 0 && w > 0 && ho > 0 && wo > 0, "grid_sample_fwd: bad dims");
   cudaStream_t s = (cudaStream_t)stream;
   bool al16 = ((((uintptr_t)grid) | ((uintptr_t)out0) | ((uintptr_t)(nimg == 2 ? out1 : out0))) & 15) == 0;
-  if (wo % 4 == 0 && al16) {
+  static const int variant = [] { const char* e = getenv("NEMAR_GS_VARIANT"); return e ? atoi(e) : 1; }();
+  if (variant == 1 && (((uintptr_t)grid) & 7) == 0) {
+    int64_t total = (int64_t)n * ho * wo;
+    grid_sample_fwd_shared_kernel<<<grid_for(total, 256), 256, 0, s>>>(img0, img1, nimg, n, c, h, w, grid, ho, wo, out0,
+                                                                      out1, idx_dump);
+  } else if (wo % 4 == 0 && al16) {
     int64_t total = (int64_t)n * ho * (wo / 4);
     grid_sample_fwd_kernel<4><<<grid_for(total, 256), 256, 0, s>>>(img0, img1, nimg, n, c, h, w, grid, ho,
                                                                     wo, out0, out1, idx_dump);
