@@ -238,57 +238,76 @@ grid_sample_fwd_kernel(const float* __restrict__ img0, const float* __restrict__
 
 // One output point per lane: for a smooth field the east taps of lane L are the west taps of lane L+1, so each lane
 // fetches only its west column (nw, sw) and receives the east column (ne, se) from its right neighbour by shuffle
-// (falling back to its own loads when the neighbour samples elsewhere).  Gathers of a warp are then contiguous
-// (one or two L1 wavefronts per request instead of four) and half as many.
+// (falling back to its own loads when the neighbour samples elsewhere).  Channel and image loops are unrolled at
+// compile time so that all west-column loads of a point are in flight together (the kernel is latency-bound, not
+// LSU-bound: measured), and the index arithmetic is 32-bit.
+template <int C, int NIMG>
 __global__ void __launch_bounds__(256)
-grid_sample_fwd_shared_kernel(const float* __restrict__ img0, const float* __restrict__ img1, int nimg, int n, int c,
-                              int h, int w, const float* __restrict__ grid, int ho, int wo, float* __restrict__ out0,
+grid_sample_fwd_shared_kernel(const float* __restrict__ img0, const float* __restrict__ img1, int n, int h, int w,
+                              const float* __restrict__ grid, int ho, int wo, float* __restrict__ out0,
                               float* __restrict__ out1, int32_t* __restrict__ idx) {
-  const int64_t ihw = (int64_t)h * w, ohw = (int64_t)ho * wo;
-  const int64_t total = (int64_t)n * ohw;
-  const int64_t total_r = (total + 31) / 32 * 32;
+  const uint32_t ihw = (uint32_t)h * w, ohw = (uint32_t)ho * wo;
+  const uint32_t total = (uint32_t)n * ohw;                 // host guarantees < 2^31
+  const uint32_t total_r = (total + 31u) & ~31u;
   const int lane = threadIdx.x & 31;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total_r; i += (int64_t)gridDim.x * blockDim.x) {
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total_r; i += gridDim.x * blockDim.x) {
     const bool active = i < total;
-    const int64_t ii = active ? i : total - 1;
-    const int64_t opix = ii % ohw;
-    const int nn = (int)(ii / ohw);
+    const uint32_t ii = active ? i : total - 1;
+    const uint32_t nn = ii / ohw;
+    const uint32_t opix = ii - nn * ohw;
     const float2 g = __ldg(reinterpret_cast<const float2*>(grid) + ii);
     const Taps t = make_taps(g.x, g.y, w, h);
-    if (idx && active) { idx[ii * 2] = t.x0; idx[ii * 2 + 1] = t.y0; }
+    if (idx && active) { idx[(size_t)ii * 2] = t.x0; idx[(size_t)ii * 2 + 1] = t.y0; }
     const int x0 = t.x0, y0 = t.y0;
     const bool xin0 = (x0 >= 0) & (x0 < w), xin1 = (x0 + 1 >= 0) & (x0 + 1 < w);
     const bool yin0 = (y0 >= 0) & (y0 < h), yin1 = (y0 + 1 >= 0) & (y0 + 1 < h);
-    // can I take my east column from the next lane's west column?
     const int nx0 = __shfl_down_sync(0xffffffffu, x0, 1);
     const int ny0 = __shfl_down_sync(0xffffffffu, y0, 1);
-    const int nnn = __shfl_down_sync(0xffffffffu, nn, 1);
+    const uint32_t nnn = __shfl_down_sync(0xffffffffu, nn, 1);
     const bool borrow = lane < 31 && nnn == nn && ny0 == y0 && nx0 == x0 + 1;
-    for (int im = 0; im < nimg; ++im) {
-      const float* img = (im == 0 ? img0 : img1) + (int64_t)nn * c * ihw;
-      float* out = (im == 0 ? out0 : out1) + (int64_t)nn * c * ohw + opix;
-      for (int ch = 0; ch < c; ++ch) {
-        const float* pl = img + ch * ihw;
-        float vnw = 0.f, vsw = 0.f;
-        if (xin0) {
-          if (yin0) vnw = __ldg(pl + (int64_t)y0 * w + x0);
-          if (yin1) vsw = __ldg(pl + (int64_t)(y0 + 1) * w + x0);
+    const size_t ibase = (size_t)nn * C * ihw;
+    const int o_nw = y0 * w + x0, o_sw = o_nw + w;
+    float vnw[NIMG][C], vsw[NIMG][C], vne[NIMG][C], vse[NIMG][C];
+#pragma unroll
+    for (int im = 0; im < NIMG; ++im) {
+      const float* img = (im == 0 ? img0 : img1) + ibase;
+#pragma unroll
+      for (int ch = 0; ch < C; ++ch) {
+        vnw[im][ch] = (xin0 && yin0) ? __ldg(img + (size_t)ch * ihw + o_nw) : 0.f;
+        vsw[im][ch] = (xin0 && yin1) ? __ldg(img + (size_t)ch * ihw + o_sw) : 0.f;
+      }
+    }
+#pragma unroll
+    for (int im = 0; im < NIMG; ++im)
+#pragma unroll
+      for (int ch = 0; ch < C; ++ch) {
+        vne[im][ch] = __shfl_down_sync(0xffffffffu, vnw[im][ch], 1);
+        vse[im][ch] = __shfl_down_sync(0xffffffffu, vsw[im][ch], 1);
+      }
+    if (!borrow) {
+#pragma unroll
+      for (int im = 0; im < NIMG; ++im) {
+        const float* img = (im == 0 ? img0 : img1) + ibase;
+#pragma unroll
+        for (int ch = 0; ch < C; ++ch) {
+          vne[im][ch] = (xin1 && yin0) ? __ldg(img + (size_t)ch * ihw + o_nw + 1) : 0.f;
+          vse[im][ch] = (xin1 && yin1) ? __ldg(img + (size_t)ch * ihw + o_sw + 1) : 0.f;
         }
-        float vne = __shfl_down_sync(0xffffffffu, vnw, 1);
-        float vse = __shfl_down_sync(0xffffffffu, vsw, 1);
-        if (!borrow) {
-          vne = 0.f; vse = 0.f;
-          if (xin1) {
-            if (yin0) vne = __ldg(pl + (int64_t)y0 * w + x0 + 1);
-            if (yin1) vse = __ldg(pl + (int64_t)(y0 + 1) * w + x0 + 1);
-          }
+      }
+    }
+    if (active) {
+#pragma unroll
+      for (int im = 0; im < NIMG; ++im) {
+        float* out = (im == 0 ? out0 : out1) + (size_t)nn * C * ohw + opix;
+#pragma unroll
+        for (int ch = 0; ch < C; ++ch) {
+          // same accumulation order as ATen's kernel: nw, ne, sw, se (out-of-range taps hold 0 and add exactly 0)
+          float acc = vnw[im][ch] * t.nw;
+          acc += vne[im][ch] * t.ne;
+          acc += vsw[im][ch] * t.sw;
+          acc += vse[im][ch] * t.se;
+          out[(size_t)ch * ohw] = acc;
         }
-        // same accumulation order as ATen's kernel: nw, ne, sw, se (out-of-range taps hold 0 and add exactly 0)
-        float acc = vnw * t.nw;
-        acc += vne * t.ne;
-        acc += vsw * t.sw;
-        acc += vse * t.se;
-        if (active) out[ch * ohw] = acc;
       }
     }
   }
@@ -303,10 +322,13 @@ NEMAR_API int nemar_grid_sample_fwd(const float* img0, const float* img1, int ni
   cudaStream_t s = (cudaStream_t)stream;
   bool al16 = ((((uintptr_t)grid) | ((uintptr_t)out0) | ((uintptr_t)(nimg == 2 ? out1 : out0))) & 15) == 0;
   static const int variant = [] { const char* e = getenv("NEMAR_GS_VARIANT"); return e ? atoi(e) : 1; }();
-  if (variant == 1 && (((uintptr_t)grid) & 7) == 0) {
-    int64_t total = (int64_t)n * ho * wo;
-    grid_sample_fwd_shared_kernel<<<grid_for(total, 256), 256, 0, s>>>(img0, img1, nimg, n, c, h, w, grid, ho, wo, out0,
-                                                                      out1, idx_dump);
+  const int64_t tot = (int64_t)n * ho * wo;
+  if (variant == 1 && c == 3 && (((uintptr_t)grid) & 7) == 0 && tot < (1ll << 31) && (int64_t)h * w < (1ll << 30)) {
+    const int blocks = grid_for(tot, 256, 148 * 16);
+    if (nimg == 2)
+      grid_sample_fwd_shared_kernel<3, 2><<<blocks, 256, 0, s>>>(img0, img1, n, h, w, grid, ho, wo, out0, out1, idx_dump);
+    else
+      grid_sample_fwd_shared_kernel<3, 1><<<blocks, 256, 0, s>>>(img0, img1, n, h, w, grid, ho, wo, out0, out1, idx_dump);
   } else if (wo % 4 == 0 && al16) {
     int64_t total = (int64_t)n * ho * (wo / 4);
     grid_sample_fwd_kernel<4><<<grid_for(total, 256), 256, 0, s>>>(img0, img1, nimg, n, c, h, w, grid, ho,
