@@ -241,7 +241,7 @@ grid_sample_fwd_kernel(const float* __restrict__ img0, const float* __restrict__
 // (falling back to its own loads when the neighbour samples elsewhere).  Channel and image loops are unrolled at
 // compile time so that all west-column loads of a point are in flight together (the kernel is latency-bound, not
 // LSU-bound: measured), and the index arithmetic is 32-bit.
-template <int C, int NIMG>
+template <int C, int NIMG, int P>
 __global__ void __launch_bounds__(256)
 grid_sample_fwd_shared_kernel(const float* __restrict__ img0, const float* __restrict__ img1, int n, int h, int w,
                               const float* __restrict__ grid, int ho, int wo, float* __restrict__ out0,
@@ -249,64 +249,85 @@ grid_sample_fwd_shared_kernel(const float* __restrict__ img0, const float* __res
   const uint32_t ihw = (uint32_t)h * w, ohw = (uint32_t)ho * wo;
   const uint32_t total = (uint32_t)n * ohw;                 // host guarantees < 2^31
   const uint32_t total_r = (total + 31u) & ~31u;
+  const uint32_t step = gridDim.x * blockDim.x;
   const int lane = threadIdx.x & 31;
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total_r; i += gridDim.x * blockDim.x) {
-    const bool active = i < total;
-    const uint32_t ii = active ? i : total - 1;
-    const uint32_t nn = ii / ohw;
-    const uint32_t opix = ii - nn * ohw;
-    const float2 g = __ldg(reinterpret_cast<const float2*>(grid) + ii);
-    const Taps t = make_taps(g.x, g.y, w, h);
-    if (idx && active) { idx[(size_t)ii * 2] = t.x0; idx[(size_t)ii * 2 + 1] = t.y0; }
-    const int x0 = t.x0, y0 = t.y0;
-    const bool xin0 = (x0 >= 0) & (x0 < w), xin1 = (x0 + 1 >= 0) & (x0 + 1 < w);
-    const bool yin0 = (y0 >= 0) & (y0 < h), yin1 = (y0 + 1 >= 0) & (y0 + 1 < h);
-    const int nx0 = __shfl_down_sync(0xffffffffu, x0, 1);
-    const int ny0 = __shfl_down_sync(0xffffffffu, y0, 1);
-    const uint32_t nnn = __shfl_down_sync(0xffffffffu, nn, 1);
-    const bool borrow = lane < 31 && nnn == nn && ny0 == y0 && nx0 == x0 + 1;
-    const size_t ibase = (size_t)nn * C * ihw;
-    const int o_nw = y0 * w + x0, o_sw = o_nw + w;
-    float vnw[NIMG][C], vsw[NIMG][C], vne[NIMG][C], vse[NIMG][C];
+  // P independent points per thread per iteration (warp-uniform trip count): all their loads are in flight together
+  for (uint32_t i0 = blockIdx.x * blockDim.x + threadIdx.x; i0 < total_r; i0 += P * step) {
+    uint32_t ii[P], nn[P], opix[P];
+    bool active[P], live[P];
+    float2 g[P];
 #pragma unroll
-    for (int im = 0; im < NIMG; ++im) {
-      const float* img = (im == 0 ? img0 : img1) + ibase;
-#pragma unroll
-      for (int ch = 0; ch < C; ++ch) {
-        vnw[im][ch] = (xin0 && yin0) ? __ldg(img + (size_t)ch * ihw + o_nw) : 0.f;
-        vsw[im][ch] = (xin0 && yin1) ? __ldg(img + (size_t)ch * ihw + o_sw) : 0.f;
-      }
+    for (int p = 0; p < P; ++p) {
+      const uint32_t i = i0 + p * step;
+      live[p] = i < total_r;                                  // warp-uniform
+      active[p] = i < total;
+      ii[p] = active[p] ? i : total - 1;
+      g[p] = __ldg(reinterpret_cast<const float2*>(grid) + ii[p]);
     }
+    Taps t[P];
+    bool borrow[P], xin0[P], xin1[P], yin0[P], yin1[P];
+    int o_nw[P];
+    float vnw[P][NIMG][C], vsw[P][NIMG][C], vne[P][NIMG][C], vse[P][NIMG][C];
 #pragma unroll
-    for (int im = 0; im < NIMG; ++im)
-#pragma unroll
-      for (int ch = 0; ch < C; ++ch) {
-        vne[im][ch] = __shfl_down_sync(0xffffffffu, vnw[im][ch], 1);
-        vse[im][ch] = __shfl_down_sync(0xffffffffu, vsw[im][ch], 1);
-      }
-    if (!borrow) {
+    for (int p = 0; p < P; ++p) {
+      nn[p] = ii[p] / ohw;
+      opix[p] = ii[p] - nn[p] * ohw;
+      t[p] = make_taps(g[p].x, g[p].y, w, h);
+      if (idx && active[p]) { idx[(size_t)ii[p] * 2] = t[p].x0; idx[(size_t)ii[p] * 2 + 1] = t[p].y0; }
+      const int x0 = t[p].x0, y0 = t[p].y0;
+      xin0[p] = (x0 >= 0) & (x0 < w); xin1[p] = (x0 + 1 >= 0) & (x0 + 1 < w);
+      yin0[p] = (y0 >= 0) & (y0 < h); yin1[p] = (y0 + 1 >= 0) & (y0 + 1 < h);
+      o_nw[p] = y0 * w + x0;
+      const size_t ibase = (size_t)nn[p] * C * ihw;
 #pragma unroll
       for (int im = 0; im < NIMG; ++im) {
         const float* img = (im == 0 ? img0 : img1) + ibase;
 #pragma unroll
         for (int ch = 0; ch < C; ++ch) {
-          vne[im][ch] = (xin1 && yin0) ? __ldg(img + (size_t)ch * ihw + o_nw + 1) : 0.f;
-          vse[im][ch] = (xin1 && yin1) ? __ldg(img + (size_t)ch * ihw + o_sw + 1) : 0.f;
+          vnw[p][im][ch] = (xin0[p] && yin0[p]) ? __ldg(img + (size_t)ch * ihw + o_nw[p]) : 0.f;
+          vsw[p][im][ch] = (xin0[p] && yin1[p]) ? __ldg(img + (size_t)ch * ihw + o_nw[p] + w) : 0.f;
         }
       }
     }
-    if (active) {
 #pragma unroll
-      for (int im = 0; im < NIMG; ++im) {
-        float* out = (im == 0 ? out0 : out1) + (size_t)nn * C * ohw + opix;
+    for (int p = 0; p < P; ++p) {
+      if (!live[p]) continue;                                 // warp-uniform: safe around the shuffles
+      const int nx0 = __shfl_down_sync(0xffffffffu, t[p].x0, 1);
+      const int ny0 = __shfl_down_sync(0xffffffffu, t[p].y0, 1);
+      const uint32_t nnn = __shfl_down_sync(0xffffffffu, nn[p], 1);
+      borrow[p] = lane < 31 && nnn == nn[p] && ny0 == t[p].y0 && nx0 == t[p].x0 + 1;
+#pragma unroll
+      for (int im = 0; im < NIMG; ++im)
 #pragma unroll
         for (int ch = 0; ch < C; ++ch) {
-          // same accumulation order as ATen's kernel: nw, ne, sw, se (out-of-range taps hold 0 and add exactly 0)
-          float acc = vnw[im][ch] * t.nw;
-          acc += vne[im][ch] * t.ne;
-          acc += vsw[im][ch] * t.sw;
-          acc += vse[im][ch] * t.se;
-          out[(size_t)ch * ohw] = acc;
+          vne[p][im][ch] = __shfl_down_sync(0xffffffffu, vnw[p][im][ch], 1);
+          vse[p][im][ch] = __shfl_down_sync(0xffffffffu, vsw[p][im][ch], 1);
+        }
+      if (!borrow[p]) {
+        const size_t ibase = (size_t)nn[p] * C * ihw;
+#pragma unroll
+        for (int im = 0; im < NIMG; ++im) {
+          const float* img = (im == 0 ? img0 : img1) + ibase;
+#pragma unroll
+          for (int ch = 0; ch < C; ++ch) {
+            vne[p][im][ch] = (xin1[p] && yin0[p]) ? __ldg(img + (size_t)ch * ihw + o_nw[p] + 1) : 0.f;
+            vse[p][im][ch] = (xin1[p] && yin1[p]) ? __ldg(img + (size_t)ch * ihw + o_nw[p] + w + 1) : 0.f;
+          }
+        }
+      }
+      if (active[p]) {
+#pragma unroll
+        for (int im = 0; im < NIMG; ++im) {
+          float* out = (im == 0 ? out0 : out1) + (size_t)nn[p] * C * ohw + opix[p];
+#pragma unroll
+          for (int ch = 0; ch < C; ++ch) {
+            // same accumulation order as ATen's kernel: nw, ne, sw, se (out-of-range taps hold 0 and add exactly 0)
+            float acc = vnw[p][im][ch] * t[p].nw;
+            acc += vne[p][im][ch] * t[p].ne;
+            acc += vsw[p][im][ch] * t[p].sw;
+            acc += vse[p][im][ch] * t[p].se;
+            out[(size_t)ch * ohw] = acc;
+          }
         }
       }
     }
@@ -324,11 +345,11 @@ NEMAR_API int nemar_grid_sample_fwd(const float* img0, const float* img1, int ni
   static const int variant = [] { const char* e = getenv("NEMAR_GS_VARIANT"); return e ? atoi(e) : 1; }();
   const int64_t tot = (int64_t)n * ho * wo;
   if (variant == 1 && c == 3 && (((uintptr_t)grid) & 7) == 0 && tot < (1ll << 31) && (int64_t)h * w < (1ll << 30)) {
-    const int blocks = grid_for(tot, 256, 148 * 16);
+    const int blocks = grid_for((tot + 1) / 2, 256, 148 * 16);
     if (nimg == 2)
-      grid_sample_fwd_shared_kernel<3, 2><<<blocks, 256, 0, s>>>(img0, img1, n, h, w, grid, ho, wo, out0, out1, idx_dump);
+      grid_sample_fwd_shared_kernel<3, 2, 2><<<blocks, 256, 0, s>>>(img0, img1, n, h, w, grid, ho, wo, out0, out1, idx_dump);
     else
-      grid_sample_fwd_shared_kernel<3, 1><<<blocks, 256, 0, s>>>(img0, img1, n, h, w, grid, ho, wo, out0, out1, idx_dump);
+      grid_sample_fwd_shared_kernel<3, 1, 2><<<blocks, 256, 0, s>>>(img0, img1, n, h, w, grid, ho, wo, out0, out1, idx_dump);
   } else if (wo % 4 == 0 && al16) {
     int64_t total = (int64_t)n * ho * (wo / 4);
     grid_sample_fwd_kernel<4><<<grid_for(total, 256), 256, 0, s>>>(img0, img1, nimg, n, c, h, w, grid, ho,
@@ -439,6 +460,109 @@ grid_sample_bwd_kernel(const float* __restrict__ img0, const float* __restrict__
   }
 }
 
+// Backward with the same one-point-per-lane layout: west-column values are loaded once and the east column is taken
+// from the right neighbour (needed for grad_grid); the scatter-add merges east contributions into the neighbour's
+// west REDs.  Channel / image loops are compile-time, indices 32-bit.
+template <int C, int NIMG>
+__global__ void __launch_bounds__(256)
+grid_sample_bwd_shared_kernel(const float* __restrict__ img0, const float* __restrict__ img1, int n, int h, int w,
+                              const float* __restrict__ grid, int ho, int wo, const float* __restrict__ dout0,
+                              const float* __restrict__ dout1, float* __restrict__ dimg0, float* __restrict__ dimg1,
+                              float* __restrict__ dgrid) {
+  const uint32_t ihw = (uint32_t)h * w, ohw = (uint32_t)ho * wo;
+  const uint32_t total = (uint32_t)n * ohw;
+  const uint32_t total_r = (total + 31u) & ~31u;
+  const int lane = threadIdx.x & 31;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total_r; i += gridDim.x * blockDim.x) {
+    const bool active = i < total;
+    const uint32_t ii = active ? i : total - 1;
+    const uint32_t nn = ii / ohw;
+    const uint32_t opix = ii - nn * ohw;
+    const float2 g = __ldg(reinterpret_cast<const float2*>(grid) + ii);
+    const Taps t = make_taps(g.x, g.y, w, h);
+    const int x0 = t.x0, y0 = t.y0;
+    const bool xin0 = (x0 >= 0) & (x0 < w), xin1 = (x0 + 1 >= 0) & (x0 + 1 < w);
+    const bool yin0 = (y0 >= 0) & (y0 < h), yin1 = (y0 + 1 >= 0) & (y0 + 1 < h);
+    const float fx = (float)x0, fy = (float)y0, x1 = fx + 1.f, y1 = fy + 1.f;
+    const size_t ibase = (size_t)nn * C * ihw;
+    const int o_nw = y0 * w + x0;
+    float vnw[NIMG][C], vsw[NIMG][C], vne[NIMG][C], vse[NIMG][C], go[NIMG][C];
+#pragma unroll
+    for (int im = 0; im < NIMG; ++im) {
+      const float* img = (im == 0 ? img0 : img1) + ibase;
+      const float* dout = (im == 0 ? dout0 : dout1) + (size_t)nn * C * ohw + opix;
+#pragma unroll
+      for (int ch = 0; ch < C; ++ch) {
+        go[im][ch] = active ? __ldg(dout + (size_t)ch * ohw) : 0.f;
+        vnw[im][ch] = (xin0 && yin0) ? __ldg(img + (size_t)ch * ihw + o_nw) : 0.f;
+        vsw[im][ch] = (xin0 && yin1) ? __ldg(img + (size_t)ch * ihw + o_nw + w) : 0.f;
+      }
+    }
+    // right neighbour: source of my east values; left neighbour: adopts my east contributions
+    const int nx0 = __shfl_down_sync(0xffffffffu, x0, 1), ny0 = __shfl_down_sync(0xffffffffu, y0, 1);
+    const uint32_t nnn = __shfl_down_sync(0xffffffffu, nn, 1);
+    const int nact = __shfl_down_sync(0xffffffffu, (int)active, 1);
+    const bool borrow = lane < 31 && nnn == nn && ny0 == y0 && nx0 == x0 + 1;     // values (any neighbour, even inactive)
+    const bool donated = borrow && active && nact;                                // my east REDs are issued by lane+1
+    const int px0 = __shfl_up_sync(0xffffffffu, x0, 1), py0 = __shfl_up_sync(0xffffffffu, y0, 1);
+    const uint32_t pnn = __shfl_up_sync(0xffffffffu, nn, 1);
+    const int pact = __shfl_up_sync(0xffffffffu, (int)active, 1);
+    const bool adopt = active && lane > 0 && pact && pnn == nn && py0 == y0 && px0 + 1 == x0;
+#pragma unroll
+    for (int im = 0; im < NIMG; ++im)
+#pragma unroll
+      for (int ch = 0; ch < C; ++ch) {
+        vne[im][ch] = __shfl_down_sync(0xffffffffu, vnw[im][ch], 1);
+        vse[im][ch] = __shfl_down_sync(0xffffffffu, vsw[im][ch], 1);
+      }
+    if (!borrow) {
+#pragma unroll
+      for (int im = 0; im < NIMG; ++im) {
+        const float* img = (im == 0 ? img0 : img1) + ibase;
+#pragma unroll
+        for (int ch = 0; ch < C; ++ch) {
+          vne[im][ch] = (xin1 && yin0) ? __ldg(img + (size_t)ch * ihw + o_nw + 1) : 0.f;
+          vse[im][ch] = (xin1 && yin1) ? __ldg(img + (size_t)ch * ihw + o_nw + w + 1) : 0.f;
+        }
+      }
+    }
+    float gix = 0.f, giy = 0.f;
+#pragma unroll
+    for (int im = 0; im < NIMG; ++im) {
+      float* dimg = (im == 0 ? dimg0 : dimg1);
+#pragma unroll
+      for (int ch = 0; ch < C; ++ch) {
+        const float gg = go[im][ch];
+        gix -= vnw[im][ch] * (y1 - t.iy) * gg;
+        giy -= vnw[im][ch] * (x1 - t.ix) * gg;
+        gix += vne[im][ch] * (y1 - t.iy) * gg;
+        giy -= vne[im][ch] * (t.ix - fx) * gg;
+        gix -= vsw[im][ch] * (t.iy - fy) * gg;
+        giy += vsw[im][ch] * (x1 - t.ix) * gg;
+        gix += vse[im][ch] * (t.iy - fy) * gg;
+        giy += vse[im][ch] * (t.ix - fx) * gg;
+        if (dimg) {   // kernel argument: warp-uniform
+          float cnw = t.nw * gg, cne = t.ne * gg, csw = t.sw * gg, cse = t.se * gg;
+          const float pne = __shfl_up_sync(0xffffffffu, cne, 1);
+          const float pse = __shfl_up_sync(0xffffffffu, cse, 1);
+          if (adopt) { cnw += pne; csw += pse; }
+          if (active) {
+            float* dp = dimg + ibase + (size_t)ch * ihw + o_nw;
+            if (xin0 && yin0) atomicAdd(dp, cnw);
+            if (xin0 && yin1) atomicAdd(dp + w, csw);
+            if (!donated) {
+              if (xin1 && yin0) atomicAdd(dp + 1, cne);
+              if (xin1 && yin1) atomicAdd(dp + w + 1, cse);
+            }
+          }
+        }
+      }
+    }
+    if (active)
+      reinterpret_cast<float2*>(dgrid)[ii] = make_float2(((float)w / 2.f) * gix, ((float)h / 2.f) * giy);
+  }
+}
+
 NEMAR_API int nemar_grid_sample_bwd(const float* img0, const float* img1, int nimg, int n, int c, int h,
                                     int w, const float* grid, int ho, int wo, const float* dout0,
                                     const float* dout1, float* dimg0, float* dimg1, float* dgrid,
@@ -449,6 +573,18 @@ NEMAR_API int nemar_grid_sample_bwd(const float* img0, const float* img1, int ni
   // the kernel treats dimg as warp-uniform per image; it handles one "has dimg" flag per image by
   // running images with/without gradient in the same loop (pointer may be NULL per image).
   int64_t total = (int64_t)n * ho * wo;
+  static const int variant = [] { const char* e = getenv("NEMAR_GS_VARIANT"); return e ? atoi(e) : 1; }();
+  if (variant == 1 && c == 3 && total < (1ll << 31) && (int64_t)h * w < (1ll << 30)) {
+    const int blocks = grid_for(total, 256, 148 * 16);
+    if (nimg == 2)
+      grid_sample_bwd_shared_kernel<3, 2><<<blocks, 256, 0, (cudaStream_t)stream>>>(img0, img1, n, h, w, grid, ho, wo, dout0,
+                                                                                     dout1, dimg0, dimg1, dgrid);
+    else
+      grid_sample_bwd_shared_kernel<3, 1><<<blocks, 256, 0, (cudaStream_t)stream>>>(img0, img1, n, h, w, grid, ho, wo, dout0,
+                                                                                     dout1, dimg0, dimg1, dgrid);
+    NEMAR_LAUNCH_CHECK();
+    return 0;
+  }
   grid_sample_bwd_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
       img0, img1, nimg, n, c, h, w, grid, ho, wo, dout0, dout1, dimg0, dimg1, dgrid);
   NEMAR_LAUNCH_CHECK();
