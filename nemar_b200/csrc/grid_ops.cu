@@ -345,11 +345,11 @@ NEMAR_API int nemar_grid_sample_fwd(const float* img0, const float* img1, int ni
   static const int variant = [] { const char* e = getenv("NEMAR_GS_VARIANT"); return e ? atoi(e) : 1; }();
   const int64_t tot = (int64_t)n * ho * wo;
   if (variant == 1 && c == 3 && (((uintptr_t)grid) & 7) == 0 && tot < (1ll << 31) && (int64_t)h * w < (1ll << 30)) {
-    const int blocks = grid_for((tot + 1) / 2, 256, 148 * 16);
+    const int blocks = grid_for(tot, 256, 148 * 16);   // P = 2 points per thread was measured slower (61 -> 70 us)
     if (nimg == 2)
-      grid_sample_fwd_shared_kernel<3, 2, 2><<<blocks, 256, 0, s>>>(img0, img1, n, h, w, grid, ho, wo, out0, out1, idx_dump);
+      grid_sample_fwd_shared_kernel<3, 2, 1><<<blocks, 256, 0, s>>>(img0, img1, n, h, w, grid, ho, wo, out0, out1, idx_dump);
     else
-      grid_sample_fwd_shared_kernel<3, 1, 2><<<blocks, 256, 0, s>>>(img0, img1, n, h, w, grid, ho, wo, out0, out1, idx_dump);
+      grid_sample_fwd_shared_kernel<3, 1, 1><<<blocks, 256, 0, s>>>(img0, img1, n, h, w, grid, ho, wo, out0, out1, idx_dump);
   } else if (wo % 4 == 0 && al16) {
     int64_t total = (int64_t)n * ho * (wo / 4);
     grid_sample_fwd_kernel<4><<<grid_for(total, 256), 256, 0, s>>>(img0, img1, nimg, n, c, h, w, grid, ho,
