@@ -75,14 +75,14 @@ class ClockSampler:
 
 
 def build_engine_model(per_gpu_batch, size=HW, precision="bf16", conv_engine="auto", netG="resnet_9blocks",
-                       stn_type="unet"):
+                       stn_type="unet", extra=()):
     from nemar_b200.engine import functional as F
     from nemar_b200.models import create_model
     from nemar_b200.options.train_options import TrainOptions
     argv = ["--dataroot", "none", "--name", "bench", "--checkpoints_dir", "/tmp/nemar_b200_bench", "--gpu_ids",
             str(int(os.environ.get("LOCAL_RANK", "0"))), "--gan_mode", "lsgan", "--no_dropout", "--stn_type", stn_type,
             "--netG", netG, "--img_height", str(size), "--img_width", str(size), "--batch_size", str(per_gpu_batch),
-            "--dataset_mode", "synthetic", "--precision", precision, "--conv_engine", conv_engine]
+            "--dataset_mode", "synthetic", "--precision", precision, "--conv_engine", conv_engine] + list(extra)
     opt = TrainOptions().parse(argv, quiet=True)
     torch.manual_seed(0)          # identical initial replicas on every rank
     model = create_model(opt)
@@ -99,7 +99,13 @@ def run_engine(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     peaks = load_peaks()
-    model, opt = build_engine_model(args.batch, args.size, args.precision, args.conv_engine)
+    extra = []
+    if args.multi_resolution > 1:
+        extra += ["--multi_resolution", str(args.multi_resolution)]
+    if args.lambda_smooth > 0:
+        extra += ["--lambda_smooth", str(args.lambda_smooth), "--stn_bilateral_alpha", str(args.alpha), "--stn_multires_reg",
+                  str(args.multires_reg)]
+    model, opt = build_engine_model(args.batch, args.size, args.precision, args.conv_engine, extra=extra)
     # the global batch is drawn once (seed 1) and sliced by rank so that 1-GPU and N-GPU runs see the same data
     g = torch.Generator().manual_seed(1)
     A_all = torch.rand((args.batch * world, 3, args.size, args.size), generator=g) * 2 - 1
@@ -176,7 +182,8 @@ def run_engine(args):
            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": round(ms / args.steps, 3),
            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
            "config": {"workload": WORKLOAD if (args.size == HW and args.batch == PER_GPU_BATCH) else
-                      "%dx%d unet STN + resnet_9blocks, batch %d/GPU" % (args.size, args.size, args.batch),
+                      "%dx%d unet STN + resnet_9blocks, batch %d/GPU, multi_resolution %d, lambda_smooth %g alpha %g" % (
+                          args.size, args.size, args.batch, args.multi_resolution, args.lambda_smooth, args.alpha),
                       "global_batch": global_batch, "parallelism": "dp%d" % world, "conv_engine": args.conv_engine,
                       "l2": "inputs larger than L2: a step streams several GB of activations, no flush needed",
                       "allreduce_per_step": 2},
@@ -326,6 +333,10 @@ def main():
     ap.add_argument("--precision", type=str, default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--conv_engine", type=str, default="auto", choices=["auto", "generic"])
     ap.add_argument("--no_cpu_baseline", action="store_true")
+    ap.add_argument("--multi_resolution", type=int, default=1, help="discriminator scales (C4: 3)")
+    ap.add_argument("--lambda_smooth", type=float, default=0.0, help="STN regulariser weight (C4: 200)")
+    ap.add_argument("--alpha", type=float, default=0.0, help="bilateral alpha of the smoothness term (C4: 1.0)")
+    ap.add_argument("--multires_reg", type=int, default=1)
     ap.add_argument("--kernel_timing", type=int, default=1, help="time conv launches with CUDA events (roofline)")
     ap.add_argument("--grid_sample_bench", type=int, default=1)
     ap.add_argument("--profile", action="store_true", help="for ncu runs: honour --warmup below 3 (numbers printed under a "
