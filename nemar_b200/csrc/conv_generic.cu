@@ -24,6 +24,7 @@ gather_gemm_kernel(TView src, TView dst, const void* __restrict__ wp, int w_dtyp
   const int N = dst.c, CS = src.c;
   const int taps = gg.kh * gg.kw;
   const int kchunks = (CS + TK - 1) / TK;
+  const int wbk = packed_bk(wp_cs);
 
   __shared__ float As[TK][TM + 4];
   __shared__ float Bs[TK][TN + 4];
@@ -89,7 +90,8 @@ gather_gemm_kernel(TView src, TView dst, const void* __restrict__ wp, int w_dtyp
         for (int q = 0; q < 4; ++q) {
           int ch = c0 + bk + q;
           float v = 0.f;
-          if (oc < N && ch < CS) v = ld_rt(wp, w_dtype, ((int64_t)oc * taps + tap) * wp_cs + ch);
+          if (oc < N && ch < CS)
+            v = ld_rt(wp, w_dtype, wbk ? packed_index(oc, tap, ch, N, wp_cs, wbk) : packed_index_rm(oc, tap, ch, taps, wp_cs));
           Bs[bk + q][bcol] = v;
         }
       }
@@ -215,7 +217,9 @@ __global__ void pack_kernel(const float* __restrict__ w, T* __restrict__ out, in
                              : (((int64_t)i * O + o) * kh + aa) * kw + bb;
       v = __ldg(w + widx);
     }
-    out[idx] = from_f<T>(v);
+    const int bk = packed_bk(ip);
+    const int64_t oidx = bk ? packed_index(o, a * kw + b, i, op, ip, bk) : idx;
+    out[oidx] = from_f<T>(v);
   }
 }
 

@@ -2,6 +2,21 @@
 #pragma once
 #include "common.cuh"
 
+// Packed-weight layout.  Logical index (o, tap, i) with o < O_p output rows, i < I_p reduction channels:
+//   I_p % 16 != 0 : row-major   [o][tap][i]
+//   I_p % 16 == 0 : chunk-major [tap][i / BK][o][i % BK], BK = 64 / 32 / 16 (largest dividing I_p) — every TMA weight
+//                   box (BK x BN rows) is then ONE contiguous BN*BK*2-byte region instead of BN strided 128-byte rows
+__host__ __device__ __forceinline__ int packed_bk(int ip) {
+  return (ip % 16 != 0) ? 0 : ((ip % 64 == 0) ? 64 : ((ip % 32 == 0) ? 32 : 16));
+}
+__host__ __device__ __forceinline__ int64_t packed_index(int o, int tap, int i, int op, int ip, int bk) {
+  const int kchunks = ip / bk;
+  return (((int64_t)tap * kchunks + i / bk) * op + o) * bk + (i % bk);
+}
+__host__ __device__ __forceinline__ int64_t packed_index_rm(int o, int tap, int i, int taps, int ip) {
+  return ((int64_t)o * taps + tap) * ip + i;
+}
+
 struct GatherGeom {
   int kh, kw;
   int sm;          // multiplier applied to the destination coordinate

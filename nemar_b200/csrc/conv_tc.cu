@@ -80,15 +80,15 @@ static int make_act_map(CUtensorMap* m, const nemar_tensor* t, int box_c, int bx
   return 0;
 }
 
-// 2-D weight map: rows = output channels, K contiguous; box (bk, box_rows)
+// 3-D weight map over the chunk-major pack [tap*kchunks][rows][bk]: a box (bk, box_rows, 1) is one contiguous region
 static int make_w_map(CUtensorMap* m, const void* w, int rows, int k_total, int bk, int box_rows) {
   EncodeTiledFn enc = get_encode();
   NEMAR_REQUIRE(enc, "cuTensorMapEncodeTiled unavailable");
-  cuuint64_t dims[2] = {(cuuint64_t)k_total, (cuuint64_t)rows};
-  cuuint64_t strides[1] = {(cuuint64_t)k_total * 2};
-  cuuint32_t box[2] = {(cuuint32_t)bk, (cuuint32_t)box_rows};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)w, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+  cuuint64_t dims[3] = {(cuuint64_t)bk, (cuuint64_t)rows, (cuuint64_t)(k_total / bk)};
+  cuuint64_t strides[2] = {(cuuint64_t)bk * 2, (cuuint64_t)rows * bk * 2};
+  cuuint32_t box[3] = {(cuuint32_t)bk, (cuuint32_t)box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, (void*)w, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    swizzle_for(bk), CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   NEMAR_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(weights) failed: %d", (int)r);
   return 0;
@@ -193,7 +193,7 @@ tc_gather_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
         mbar_expect_tx(&full_bar[stage], Cfg::TX_BYTES);
         tma_load_4d(sa, &tmA, &full_bar[stage], kc * BK, x0 * P.sm + P.tdx[tap], y0 * P.sm + P.tdy[tap], n0);
-        tma_load_2d(sa + Cfg::A_BYTES, &tmB, &full_bar[stage], P.twi[tap] * P.cs + kc * BK, c0);
+        tma_load_3d(sa + Cfg::A_BYTES, &tmB, &full_bar[stage], 0, c0, P.twi[tap] * P.kchunks + kc);
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
