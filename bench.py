@@ -105,6 +105,9 @@ def run_engine(args):
     if args.lambda_smooth > 0:
         extra += ["--lambda_smooth", str(args.lambda_smooth), "--stn_bilateral_alpha", str(args.alpha), "--stn_multires_reg",
                   str(args.multires_reg)]
+    if args.cuda_graph:
+        extra += ["--cuda_graph", "1"]
+        args.kernel_timing = 0
     model, opt = build_engine_model(args.batch, args.size, args.precision, args.conv_engine, extra=extra)
     # the global batch is drawn once (seed 1) and sliced by rank so that 1-GPU and N-GPU runs see the same data
     g = torch.Generator().manual_seed(1)
@@ -137,7 +140,7 @@ def run_engine(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms)
 
-    for _ in range(args.warmup if args.profile else max(args.warmup, 3)):
+    for _ in range(args.warmup if args.profile else max(args.warmup, 3) + (4 if args.cuda_graph else 0)):
         model.set_input(dev_batch)
         model.optimize_parameters()
     torch.cuda.synchronize()
@@ -186,6 +189,7 @@ def run_engine(args):
                           args.size, args.size, args.batch, args.multi_resolution, args.lambda_smooth, args.alpha),
                       "global_batch": global_batch, "parallelism": "dp%d" % world, "conv_engine": args.conv_engine,
                       "l2": "inputs larger than L2: a step streams several GB of activations, no flush needed",
+                      "cuda_graph": bool(args.cuda_graph),
                       "allreduce_per_step": 2},
            "clocks": clocks,
            "e2e": {"value": round(e2e_value, 3), "unit": "samples/s", "h2d_bytes_per_step": int(A_host.numel() * 4 * 2),
@@ -337,6 +341,7 @@ def main():
     ap.add_argument("--lambda_smooth", type=float, default=0.0, help="STN regulariser weight (C4: 200)")
     ap.add_argument("--alpha", type=float, default=0.0, help="bilateral alpha of the smoothness term (C4: 1.0)")
     ap.add_argument("--multires_reg", type=int, default=1)
+    ap.add_argument("--cuda_graph", type=int, default=0, help="capture the step in a CUDA graph (kernel timing is then off)")
     ap.add_argument("--kernel_timing", type=int, default=1, help="time conv launches with CUDA events (roofline)")
     ap.add_argument("--grid_sample_bench", type=int, default=1)
     ap.add_argument("--profile", action="store_true", help="for ncu runs: honour --warmup below 3 (numbers printed under a "

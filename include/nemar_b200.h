@@ -218,6 +218,11 @@ int nemar_linear_bwd(const float* x, const float* w, const float* y, const float
 int nemar_adam_step(float* p, const float* g, float* m, float* v, int64_t numel, float lr, float beta1,
                     float beta2, float eps, int step_count, float grad_scale, void* stream);
 
+/* Same update with the 1-based step number read from DEVICE memory (*step_dev is incremented by the call, in stream
+ * order) so that the launch can be replayed from a CUDA graph. */
+int nemar_adam_step_dev(float* p, const float* g, float* m, float* v, int64_t numel, float lr, float beta1,
+                        float beta2, float eps, int32_t* step_dev, float grad_scale, void* stream);
+
 /* Dropout(0.5) of the ResnetBlock (networks.py:427-428): counter-based mask, y = keep ? 2x : 0 */
 int nemar_dropout(const nemar_tensor* x, const nemar_tensor* y, uint64_t seed, uint64_t offset,
                   void* stream);

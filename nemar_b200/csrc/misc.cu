@@ -248,6 +248,33 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
   }
 }
 
+// graph-replayable variant: bias corrections derived on the device from a step counter kept in device memory
+__global__ void adam_dev_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                float* __restrict__ v, int64_t numel, float lr, float b1, float b2, float eps,
+                                const int32_t* __restrict__ step_dev, float gscale) {
+  const int t = *step_dev + 1;
+  const double bc1 = 1.0 - pow((double)b1, (double)t), bc2 = 1.0 - pow((double)b2, (double)t);
+  const float step_size = (float)((double)lr / bc1), inv_bc2_sqrt = (float)(1.0 / sqrt(bc2));
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < numel; i += (int64_t)gridDim.x * blockDim.x) {
+    float gr = g[i] * gscale;
+    float mm = b1 * m[i] + (1.f - b1) * gr;
+    float vv = b2 * v[i] + (1.f - b2) * gr * gr;
+    m[i] = mm; v[i] = vv;
+    p[i] -= step_size * (mm / (sqrtf(vv) * inv_bc2_sqrt + eps));
+  }
+}
+__global__ void counter_inc_kernel(int32_t* c) { *c += 1; }
+
+NEMAR_API int nemar_adam_step_dev(float* p, const float* g, float* m, float* v, int64_t numel, float lr, float beta1,
+                                  float beta2, float eps, int32_t* step_dev, float grad_scale, void* stream) {
+  NEMAR_REQUIRE(p && g && m && v && step_dev && numel > 0, "adam_step_dev: bad args");
+  cudaStream_t s = (cudaStream_t)stream;
+  adam_dev_kernel<<<grid_for(numel, 256), 256, 0, s>>>(p, g, m, v, numel, lr, beta1, beta2, eps, step_dev, grad_scale);
+  counter_inc_kernel<<<1, 1, 0, s>>>(step_dev);
+  NEMAR_LAUNCH_CHECK();
+  return 0;
+}
+
 NEMAR_API int nemar_adam_step(float* p, const float* g, float* m, float* v, int64_t numel, float lr,
                               float beta1, float beta2, float eps, int step_count, float grad_scale,
                               void* stream) {

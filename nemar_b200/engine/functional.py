@@ -643,3 +643,8 @@ class LinearFn(Function):
 def adam_step(p, g, m, v, lr, beta1, beta2, eps, step, grad_scale=1.0):
     call("nemar_adam_step", fptr(p), fptr(g), fptr(m), fptr(v), i64(p.numel()), float(lr), float(beta1), float(beta2),
          float(eps), int(step), float(grad_scale), stream())
+
+
+def adam_step_dev(p, g, m, v, lr, beta1, beta2, eps, step_dev, grad_scale=1.0):
+    call("nemar_adam_step_dev", fptr(p), fptr(g), fptr(m), fptr(v), i64(p.numel()), float(lr), float(beta1), float(beta2),
+         float(eps), vptr(step_dev), float(grad_scale), stream())

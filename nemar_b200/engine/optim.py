@@ -33,6 +33,7 @@ class FlatAdam:
                 p.data = self.flat_p[o:o + n].view(p.shape)
                 p.grad = self.flat_g[o:o + n].view(p.shape)
         self.offsets = offs
+        self.step_dev = torch.zeros(1, dtype=torch.int32, device=dev)   # device-resident step counter (CUDA-graph replay)
         # torch.optim-like surface used by BaseModel (schedulers / lr printing)
         self.param_groups = [{"params": self.params, "lr": lr, "betas": betas, "eps": eps}]
         self.grad_hook = None   # set by the data-parallel wrapper: called on flat_g before the update
@@ -50,8 +51,9 @@ class FlatAdam:
             grad_scale = self.grad_hook(self.flat_g)
         self.step_count += 1
         lr = self.param_groups[0]["lr"]
-        F.adam_step(self.flat_p, self.flat_g, self.exp_avg, self.exp_avg_sq, lr, self.betas[0], self.betas[1],
-                    self.eps, self.step_count, grad_scale)
+        # the step number lives in device memory so that a captured step replays with the right bias correction
+        F.adam_step_dev(self.flat_p, self.flat_g, self.exp_avg, self.exp_avg_sq, lr, self.betas[0], self.betas[1],
+                        self.eps, self.step_dev, grad_scale)
         F.bump_weights_epoch()
 
     def state_dict(self):
@@ -60,6 +62,7 @@ class FlatAdam:
 
     def load_state_dict(self, sd):
         self.step_count = int(sd["step"])
+        self.step_dev.fill_(self.step_count)
         self.exp_avg.copy_(sd["exp_avg"])
         self.exp_avg_sq.copy_(sd["exp_avg_sq"])
         self.param_groups[0]["lr"] = float(sd.get("lr", self.lr))
