@@ -8,6 +8,7 @@ netD attributes and checkpoint keys.  Differences that are part of the design:
   * real_A resizes for the multi-resolution discriminators are computed once per step, not five times.
 """
 import itertools
+import os
 
 import torch
 
@@ -177,7 +178,7 @@ class NEMARModel(BaseModel):
         try:
             torch.cuda.synchronize()
             graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
+            with torch.cuda.graph(graph, capture_error_mode=os.environ.get("NEMAR_GRAPH_CAPTURE_MODE", "thread_local")):
                 self._optimize_parameters_eager()
             st["graph"] = graph
             graph.replay()                    # the capture itself does not execute the step
