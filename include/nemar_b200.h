@@ -107,11 +107,12 @@ int nemar_conv2d_fprop(const nemar_tensor* x, const void* w_packed, int w_cin_p,
 /* dx = conv_dgrad(dy); dx halo (if dx->pad>0) receives the raw padded-buffer gradient. */
 int nemar_conv2d_dgrad(const nemar_tensor* dy, const void* w_packed_d, int w_cout_p,
                        const nemar_conv_geom* g, const nemar_tensor* dx, int use_tc, void* stream);
-/* dw (reference layout fp32, overwritten) = wgrad(x, dy); workspace >= nemar_conv2d_wgrad_workspace() */
+/* dw (reference layout fp32; overwritten, or accumulated into when accumulate != 0 — the flat gradient bucket of
+ * the optimizer) = wgrad(x, dy); workspace >= nemar_conv2d_wgrad_workspace() */
 int64_t nemar_conv2d_wgrad_workspace(const nemar_tensor* x, const nemar_tensor* dy,
                                      const nemar_conv_geom* g, int use_tc);
 int nemar_conv2d_wgrad(const nemar_tensor* x, const nemar_tensor* dy, const nemar_conv_geom* g,
-                       float* dw, void* workspace, int64_t workspace_bytes, int use_tc, void* stream);
+                       float* dw, void* workspace, int64_t workspace_bytes, int use_tc, int accumulate, void* stream);
 /* db[c] = sum over n,h,w of dy (overwritten) */
 int nemar_bias_grad(const nemar_tensor* dy, float* db, void* stream);
 

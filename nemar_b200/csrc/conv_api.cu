@@ -110,18 +110,20 @@ NEMAR_API int64_t nemar_conv2d_wgrad_workspace(const nemar_tensor* x, const nema
 }
 
 NEMAR_API int nemar_conv2d_wgrad(const nemar_tensor* x, const nemar_tensor* dy, const nemar_conv_geom* g,
-                                 float* dw, void* workspace, int64_t workspace_bytes, int use_tc, void* stream) {
+                                 float* dw, void* workspace, int64_t workspace_bytes, int use_tc, int accumulate,
+                                 void* stream) {
   NEMAR_REQUIRE(view_ok(x) && view_ok(dy) && dw && geom_ok(g), "conv2d_wgrad: bad args");
   NEMAR_REQUIRE(x->c >= g->cin && dy->c >= g->cout && x->n == dy->n, "conv2d_wgrad: channel mismatch");
   WgradView v = wgrad_view(x, dy, g);
   NEMAR_REQUIRE(v.dyc->pad == 0 && v.pe >= 0, "conv2d_wgrad: unsupported halo configuration");
   cudaStream_t s = (cudaStream_t)stream;
   if (use_tc && tc_wgrad_supported(v.xc, v.dyc, g->kh, g->kw, g->stride, v.pe))
-    return tc_wgrad(v.xc, v.dyc, dw, v.co_real, v.ci_real, g->kh, g->kw, g->stride, v.pe, workspace, workspace_bytes, s);
+    return tc_wgrad(v.xc, v.dyc, dw, v.co_real, v.ci_real, g->kh, g->kw, g->stride, v.pe, workspace, workspace_bytes,
+                    accumulate, s);
   // generic engine: narrow the views to the real channels (the padding holds zeros and contributes nothing)
   nemar_tensor xr = *v.xc, dr = *v.dyc;
   xr.c = v.ci_real; dr.c = v.co_real;
-  return generic_wgrad(&xr, &dr, dw, g->kh, g->kw, g->stride, v.pe, s);
+  return generic_wgrad(&xr, &dr, dw, g->kh, g->kw, g->stride, v.pe, accumulate, s);
 }
 
 NEMAR_API int nemar_conv2d_tc_supported(const nemar_conv_geom* g, int dtype, int h_in, int w_in) {

@@ -237,10 +237,10 @@ int generic_gather_gemm(const nemar_tensor* src, const nemar_tensor* dst, const 
 }
 
 int generic_wgrad(const nemar_tensor* x, const nemar_tensor* dy, float* dw, int kh, int kw, int stride, int pe,
-                  cudaStream_t s) {
+                  int accumulate, cudaStream_t s) {
   TView xv = make_view(x), dv = make_view(dy);
   const int taps = kh * kw;
-  cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)dv.c * xv.c * taps, s);
+  if (!accumulate) cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)dv.c * xv.c * taps, s);
   const int64_t P = (int64_t)dv.n * dv.h * dv.w;
   int ci_tiles = (xv.c + 31) / 32, co_tiles = (dv.c + 31) / 32;
   int64_t base_blocks = (int64_t)taps * ci_tiles * co_tiles;

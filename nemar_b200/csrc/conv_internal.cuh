@@ -29,7 +29,7 @@ struct GatherGeom {
 int generic_gather_gemm(const nemar_tensor* src, const nemar_tensor* dst, const void* wp, int w_dtype, int wp_cs,
                         const float* bias, int act, const GatherGeom& gg, cudaStream_t s);
 int generic_wgrad(const nemar_tensor* x, const nemar_tensor* dy, float* dw, int kh, int kw, int stride, int pe,
-                  cudaStream_t s);
+                  int accumulate, cudaStream_t s);
 int generic_pack(const float* w, void* out, int dtype, int O, int op, int I, int ip, int kh, int kw, int w_is_oi,
                  int flip, cudaStream_t s);
 
@@ -41,4 +41,4 @@ int tc_gather_gemm(const nemar_tensor* src, const nemar_tensor* dst, const void*
 bool tc_wgrad_supported(const nemar_tensor* x, const nemar_tensor* dy, int kh, int kw, int stride, int pe);
 int64_t tc_wgrad_workspace(const nemar_tensor* x, const nemar_tensor* dy, int kh, int kw, int stride, int pe);
 int tc_wgrad(const nemar_tensor* x, const nemar_tensor* dy, float* dw, int co_real, int ci_real, int kh, int kw, int stride,
-             int pe, void* workspace, int64_t workspace_bytes, cudaStream_t s);
+             int pe, void* workspace, int64_t workspace_bytes, int accumulate, cudaStream_t s);

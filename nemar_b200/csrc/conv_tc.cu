@@ -591,7 +591,7 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant_
 // dw[co][ci][tap] = sum_split partial[split][tap][co][ci]   (co < co_real, ci < ci_real)
 // partial is [split][tap][m_pad][n_pad]; (m,n) = (co,ci), or (ci,co) when the operand roles were swapped
 __global__ void wgrad_finalize_kernel(const float* __restrict__ partial, float* __restrict__ dw, int splits, int taps,
-                                      int co_real, int ci_real, int m_pad, int n_pad, int swapped) {
+                                      int co_real, int ci_real, int m_pad, int n_pad, int swapped, int accumulate) {
   const int64_t total = (int64_t)co_real * ci_real * taps;
   const int n_real = swapped ? co_real : ci_real;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -603,7 +603,8 @@ __global__ void wgrad_finalize_kernel(const float* __restrict__ partial, float* 
     for (int s = 0; s < splits; ++s)
       acc += __ldg(partial + (((int64_t)s * taps + tap) * m_pad + mm) * n_pad + nn);
     const int c_o = swapped ? nn : mm, c_i = swapped ? mm : nn;
-    dw[((int64_t)c_o * ci_real + c_i) * taps + tap] = acc;
+    float* o = dw + ((int64_t)c_o * ci_real + c_i) * taps + tap;
+    *o = accumulate ? *o + acc : acc;
   }
 }
 
@@ -696,7 +697,7 @@ int64_t tc_wgrad_workspace(const nemar_tensor* x, const nemar_tensor* dy, int kh
 }
 
 int tc_wgrad(const nemar_tensor* x_in, const nemar_tensor* dy, float* dw, int co_real, int ci_real, int kh, int kw,
-             int stride, int pe, void* workspace, int64_t workspace_bytes, cudaStream_t s) {
+             int stride, int pe, void* workspace, int64_t workspace_bytes, int accumulate, cudaStream_t s) {
   NEMAR_REQUIRE(tc_wgrad_supported(x_in, dy, kh, kw, stride, pe), "tc_wgrad: unsupported geometry");
   nemar_tensor x = *x_in;
   x.h += 2 * x.pad; x.w += 2 * x.pad; x.pad = 0;      // halo = real data; `pe` is relative to the padded buffer
@@ -727,7 +728,7 @@ int tc_wgrad(const nemar_tensor* x_in, const nemar_tensor* dy, float* dw, int co
   if (rc) return rc;
   const int64_t total = (int64_t)co_real * ci_real * pl.taps;
   wgrad_finalize_kernel<<<grid_for(total, 256), 256, 0, s>>>((const float*)workspace, dw, pl.splits, pl.taps, co_real,
-                                                              ci_real, pl.co_tiles * BM, P.ci, pl.swapped);
+                                                              ci_real, pl.co_tiles * BM, P.ci, pl.swapped, accumulate);
   NEMAR_LAUNCH_CHECK();
   return 0;
 }

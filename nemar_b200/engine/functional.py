@@ -27,6 +27,19 @@ def _c(t):
     return t if t.is_contiguous() else t.contiguous()
 
 
+def _deliver(param, grad):
+    """Hand a parameter gradient over.  When the parameter already owns a gradient buffer (the optimizer's flat
+    bucket), accumulate into it HERE, on the stream this backward runs on, and tell autograd there is nothing left
+    to do: no AccumulateGrad kernel is launched later on some other stream (which also keeps the whole step
+    capturable in a CUDA graph).  Otherwise return the gradient for autograd to store."""
+    if grad is None:
+        return None
+    if param is not None and param.is_leaf and param.grad is not None and param.grad.shape == grad.shape:
+        param.grad.add_(grad)
+        return None
+    return grad
+
+
 # ------------------------------------------------------------------------------------------------
 # layout crossings
 # ------------------------------------------------------------------------------------------------
@@ -197,6 +210,7 @@ class Conv2dFn(Function):
              int(cfg.use_tc), stream())
         ctx.cfg, ctx.wd = cfg, wd
         ctx.has_bias = bias is not None
+        ctx.bias_param = bias
         ctx.save_for_backward(x, weight, y if cfg.act != L.ACT_NONE else None)
         if stats is None:
             return y
@@ -221,17 +235,45 @@ class Conv2dFn(Function):
             call("nemar_conv2d_dgrad", view(gk), vptr(ctx.wd), cfg.cout_p, cfg.geom, view(dx, cfg.x_pad), int(cfg.use_tc),
                  stream())
         if ctx.needs_input_grad[1]:
-            dw = torch.empty(weight.shape, dtype=torch.float32, device=x.device)
+            direct = weight.is_leaf and weight.grad is not None and weight.grad.is_contiguous()
+            dw = weight.grad if direct else torch.empty(weight.shape, dtype=torch.float32, device=x.device)
             xv, gv = view(x, cfg.x_pad), view(gk)
             ws_bytes = L.lib().nemar_conv2d_wgrad_workspace(L.C.byref(xv), L.C.byref(gv), L.C.byref(cfg.geom),
                                                             int(cfg.use_tc))
             ws = torch.empty(max(int(ws_bytes), 16), dtype=torch.uint8, device=x.device) if ws_bytes > 0 else None
-            call("nemar_conv2d_wgrad", xv, gv, cfg.geom, fptr(dw), vptr(ws), i64(ws_bytes), int(cfg.use_tc), stream())
+            call("nemar_conv2d_wgrad", xv, gv, cfg.geom, fptr(dw), vptr(ws), i64(ws_bytes), int(cfg.use_tc), int(direct),
+                 stream())
+            if direct:
+                dw = None
         if ctx.has_bias and ctx.needs_input_grad[2] and not cfg.defer_bias_grad:
             db = torch.empty(cfg.cout_p, dtype=torch.float32, device=x.device)
             call("nemar_bias_grad", view(g), fptr(db), stream())
-            db = db[:cfg.cout]
+            db = _deliver(ctx.bias_param, db[:cfg.cout])
         return dx, dw, db, None, None
+
+
+class TapsWeightFn(Function):
+    """The k x k weight of a <=4-channel head / tail seen as the weight of the equivalent 1x1 convolution:
+    head: [co][ci][a][b] -> [co][(a,b,ci)][1][1];  tail: [co][ci][a][b] -> [(a,b,co)][ci][1][1].  A copy of a few
+    thousand elements (torch glue); the backward delivers the gradient straight into the parameter's bucket."""
+
+    @staticmethod
+    def forward(ctx, weight, mode):
+        co, ci, k, _ = weight.shape
+        ctx.meta = (mode, co, ci, k)
+        ctx.param = weight
+        if mode == "head":
+            return weight.detach().permute(0, 2, 3, 1).reshape(co, k * k * ci, 1, 1).contiguous()
+        return weight.detach().permute(2, 3, 0, 1).reshape(k * k * co, ci, 1, 1).contiguous()
+
+    @staticmethod
+    def backward(ctx, g):
+        mode, co, ci, k = ctx.meta
+        if mode == "head":
+            gw = g.reshape(co, k, k, ci).permute(0, 3, 1, 2)
+        else:
+            gw = g.reshape(k, k, co, ci).permute(2, 3, 0, 1)
+        return _deliver(ctx.param, gw), None
 
 
 class GatherTapsFn(Function):
@@ -268,6 +310,7 @@ class SumTapsFn(Function):
         y = torch.empty((n, oh, ow, cp), dtype=torch.float32, device=x.device)
         call("nemar_sum_taps", view(x), view(y), k, c, sgn, fptr(bias.detach()) if bias is not None else None, act, stream())
         ctx.meta = (k, c, sgn, x.shape, x.dtype, act, bias is not None)
+        ctx.bias_param = bias
         ctx.save_for_backward(y if act != L.ACT_NONE else None)
         return y
 
@@ -287,7 +330,7 @@ class SumTapsFn(Function):
             call("nemar_bias_grad", view(g, 0, 0, c), fptr(db), stream())
         dx = torch.empty(shape, dtype=dtype, device=dy.device)
         call("nemar_gather_taps", view(g), view(dx), k, c, sgn, stream())
-        return dx, db, None, None, None, None, None, None, None
+        return dx, _deliver(ctx.bias_param, db), None, None, None, None, None, None, None
 
 
 # ------------------------------------------------------------------------------------------------
@@ -308,6 +351,7 @@ class NormActFn(Function):
         call("nemar_norm_act_fwd", view(x), fptr(stats), act, rv, view(y, out_pad), pad_mode, stream())
         ctx.meta = (act, res_pad, out_pad, pad_mode, residual.shape if residual is not None else None,
                     bias.numel() if bias is not None else 0)
+        ctx.bias_param = bias
         ctx.save_for_backward(x, stats)
         return y
 
@@ -333,7 +377,7 @@ class NormActFn(Function):
             db = torch.empty(c, dtype=torch.float32, device=x.device)
         call("nemar_norm_act_bwd_apply", view(x), fptr(stats), act, view(dy, out_pad), pad_mode, fptr(red), view(dx),
              drv, 0, fptr(db), stream())
-        return dx, None, dres, None, None, None, None, (db[:nbias] if db is not None else None)
+        return dx, None, dres, None, None, None, None, _deliver(ctx.bias_param, db[:nbias] if db is not None else None)
 
 
 class MaxPool2Fn(Function):
@@ -623,6 +667,7 @@ class LinearFn(Function):
              fptr(y), stream())
         ctx.save_for_backward(x, w, y)
         ctx.meta = (act, b is not None)
+        ctx.params = (w, b)
         return y
 
     @staticmethod
@@ -637,7 +682,7 @@ class LinearFn(Function):
         db = torch.empty(o, dtype=torch.float32, device=x.device) if has_b else None
         call("nemar_linear_bwd", fptr(x), fptr(w.detach()), fptr(y), fptr(dy), n, i, o, act, fptr(dx), fptr(dw),
              fptr(db), stream())
-        return dx, dw, db, None
+        return dx, _deliver(ctx.params[0], dw), _deliver(ctx.params[1], db), None
 
 
 def adam_step(p, g, m, v, lr, beta1, beta2, eps, step, grad_scale=1.0):

@@ -84,7 +84,7 @@ class Conv(nn.Module):
         n, hp, wp, _ = x_padded.shape
         kc = k * k * cin
         u = F.GatherTapsFn.apply(x_padded, k, cin, 1, hp - 2 * pad, wp - 2 * pad, (kc + 31) // 32 * 32, x_padded.dtype)
-        w1 = self.weight.permute(0, 2, 3, 1).reshape(cout, kc, 1, 1)          # [co][(a,b,ci)]
+        w1 = F.TapsWeightFn.apply(self.weight, "head")                        # [co][(a,b,ci)][1][1]
         return self._run(u, w1, self.bias, (kc, cout, 1, 1, 0, False, 0), "head_taps", 0, L.ACT_NONE, stats, False, True)
 
     def run_tail_taps(self, x_padded, act, cp=4):
@@ -93,7 +93,7 @@ class Conv(nn.Module):
         cin, cout, k, _, pad, _, _ = self.meta
         n, hp, wp, _ = x_padded.shape
         kc = k * k * cout
-        wv = self.weight.permute(2, 3, 0, 1).reshape(kc, cin, 1, 1)           # [(a,b,co)][ci]
+        wv = F.TapsWeightFn.apply(self.weight, "tail")                        # [(a,b,co)][ci][1][1]
         v = self._run(x_padded, wv, None, (cin, kc, 1, 1, 0, False, 0), "tail_taps", 0, L.ACT_NONE, False, False, False)
         return F.SumTapsFn.apply(v, self.bias, k, cout, -1, hp - 2 * pad, wp - 2 * pad, cp, act)
 
