@@ -174,7 +174,14 @@ class NEMARModel(BaseModel):
             if self.__dict__.get("_graph_inputs") is None:
                 self._graph_inputs = (self.real_A.clone(), self.real_B.clone())
                 self.real_A, self.real_B = self._graph_inputs
-            return self._optimize_parameters_eager()
+            # warm up on a side stream: autograd binds every parameter's gradient accumulator to the stream that is
+            # current when it is first used, and a capture must not depend on the legacy default stream
+            side = st.setdefault("side", torch.cuda.Stream())
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                self._optimize_parameters_eager()
+            torch.cuda.current_stream().wait_stream(side)
+            return
         try:
             torch.cuda.synchronize()
             graph = torch.cuda.CUDAGraph()
