@@ -30,8 +30,9 @@ class NEMARModel(BaseModel):
         parser.add_argument("--conv_engine", type=str, default="auto", choices=["auto", "generic"],
                             help="[engine] auto: tcgen05 where supported; generic: CUDA-core kernels only")
         parser.add_argument("--cuda_graph", type=int, default=0,
-                            help="[engine] 1: capture optimize_parameters in a CUDA graph after 3 eager steps and replay it "
-                                 "(static shapes; falls back to eager launches if capture fails)")
+                            help="[engine, EXPERIMENTAL] 1: capture optimize_parameters in a CUDA graph after 3 eager steps "
+                                 "and replay it.  Capture currently aborts with cudaErrorStreamCaptureIsolation inside "
+                                 "autograd's end-of-backward stream sync (DESIGN.md section 7); leave at 0")
         if is_train:
             parser.add_argument("--lambda_GAN", type=float, default=1.0, help="weight of the GAN loss")
             parser.add_argument("--lambda_recon", type=float, default=100.0, help="weight of the L1 reconstruction loss")
