@@ -6,6 +6,13 @@
 // models/stn/unet_stn.py:96,166,188-195; models/nemar_model.py:187-188.
 #include "common.cuh"
 #include "vec.cuh"
+#include "norm_fast.cuh"
+#include <cstdlib>
+
+static bool norm_fast_enabled() {
+  static const int v = [] { const char* e = getenv("NEMAR_NORM_FAST"); return e ? atoi(e) : 1; }();
+  return v != 0;
+}
 
 // =============================================================================================
 // helpers
@@ -438,6 +445,13 @@ static int launch_plane_reduce(const nemar_tensor* xt, const float* stats, int a
   TView dy = dyt ? make_view(dyt) : x;
   const float inv_hw = 1.f / ((float)x.h * (float)x.w);
   const int64_t hw = (int64_t)x.h * x.w;
+  if (norm_fast_enabled() && nfast::eligible(xt) && (!dyt || nfast::eligible(dyt))) {
+    const int G = x.c / 8;
+    dim3 grid(nfast::chunks_for(hw, G, x.n), x.n);
+    nfast::reduce_kernel<MODE><<<grid, 256, sizeof(float) * 2 * x.c, s>>>(x, stats, act, dy, pad_mode, inv_hw, out);
+    NEMAR_LAUNCH_CHECK();
+    return 0;
+  }
   DISPATCH_DTYPE(x.dtype, T, {
     constexpr int VV = VecTraits<T>::V;
     bool vec = view_vec_ok<T>(xt) && (!dyt || view_vec_ok<T>(dyt));
@@ -604,6 +618,12 @@ NEMAR_API int nemar_norm_act_fwd(const nemar_tensor* x, const float* stats, int 
   TView xv = make_view(x), yv = make_view(y), rv = residual ? make_view(residual) : xv;
   const float inv_hw = 1.f / ((float)xv.h * (float)xv.w);
   cudaStream_t s = (cudaStream_t)stream;
+  if (norm_fast_enabled() && nfast::eligible(x) && nfast::eligible(y) && (!residual || nfast::eligible(residual))) {
+    dim3 grid(nfast::chunks_for((int64_t)yv.hp * yv.wp, yv.c / 8, yv.n), yv.n);
+    nfast::fwd_kernel<<<grid, 256, 0, s>>>(xv, stats, act, rv, residual != nullptr, yv, pad_mode, inv_hw);
+    NEMAR_LAUNCH_CHECK();
+    return 0;
+  }
   DISPATCH_DTYPE(xv.dtype, T, {
     constexpr int VV = VecTraits<T>::V;
     bool vec = view_vec_ok<T>(x) && view_vec_ok<T>(y) && (!residual || view_vec_ok<T>(residual));
@@ -725,6 +745,14 @@ NEMAR_API int nemar_norm_act_bwd_apply(const nemar_tensor* x, const float* stats
   TView xv = make_view(x), dyv = make_view(dy), dxv = make_view(dx), dr = dres ? make_view(dres) : xv;
   const float inv_hw = 1.f / ((float)xv.h * (float)xv.w);
   cudaStream_t s = (cudaStream_t)stream;
+  if (norm_fast_enabled() && nfast::eligible(x) && nfast::eligible(dy) && nfast::eligible(dx) && (!dres || nfast::eligible(dres))) {
+    if (db) cudaMemsetAsync(db, 0, sizeof(float) * xv.c, s);
+    dim3 grid(nfast::chunks_for((int64_t)xv.h * xv.w, xv.c / 8, xv.n), xv.n);
+    nfast::bwd_apply_kernel<<<grid, 256, sizeof(float) * xv.c, s>>>(xv, stats, act, dyv, pad_mode, red, dxv, dr,
+                                                                     dres != nullptr, dres_accumulate, inv_hw, db);
+    NEMAR_LAUNCH_CHECK();
+    return 0;
+  }
   DISPATCH_DTYPE(xv.dtype, T, {
     constexpr int VV = VecTraits<T>::V;
     bool vec = view_vec_ok<T>(x) && view_vec_ok<T>(dy) && view_vec_ok<T>(dx) && (!dres || view_vec_ok<T>(dres));
