@@ -185,7 +185,7 @@ def run_engine(args):
                 "share_of_timed_kernels": round(st["ms"] / max(tot_ms, 1e-9), 4),
                 "by_kernel": {k: {"ms": round(v["ms"], 3), "n": v["n"],
                                   "tflops": round(v["flops"] / max(v["ms"], 1e-9) / 1e9, 2),
-                                  "top": dict(sorted(((a, round(b, 3)) for a, b in v["top"].items()), key=lambda t: -t[1])[:4])}
+                                  "top": dict(sorted(((a, round(b, 3)) for a, b in v["top"].items()), key=lambda t: -t[1])[:args.top])}
                               for k, v in sorted(kstats.items(), key=lambda kv: -kv[1]["ms"])}}
     conv_frac = value * CONV_GFLOP_PER_SAMPLE * 1e9 / (world * peaks["tf_sustained"] * 1e12) if args.size == HW else None
     out = {"metric": "paired 256x256 samples/sec", "value": round(value, 3), "unit": "samples/s", "n_gpus": world,
@@ -349,6 +349,7 @@ def main():
     ap.add_argument("--alpha", type=float, default=0.0, help="bilateral alpha of the smoothness term (C4: 1.0)")
     ap.add_argument("--multires_reg", type=int, default=1)
     ap.add_argument("--cuda_graph", type=int, default=0, help="capture the step in a CUDA graph (kernel timing is then off)")
+    ap.add_argument("--top", type=int, default=4, help="shapes listed per kernel class in roofline.by_kernel")
     ap.add_argument("--kernel_timing", type=int, default=1, help="time conv launches with CUDA events (roofline)")
     ap.add_argument("--grid_sample_bench", type=int, default=1)
     ap.add_argument("--profile", action="store_true", help="for ncu runs: honour --warmup below 3 (numbers printed under a "

@@ -39,6 +39,15 @@ __host__ __device__ constexpr uint32_t round1k(uint32_t v) { return (v + 1023u) 
 __host__ __device__ constexpr uint64_t layout_for(int chunk_elems) {
   return chunk_elems == 64 ? LAYOUT_SW128 : (chunk_elems == 32 ? LAYOUT_SW64 : LAYOUT_SW32);
 }
+static int sm_count() {
+  static const int n = [] {
+    int dev = 0, v = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
+    return v;
+  }();
+  return n;
+}
+
 static CUtensorMapSwizzle swizzle_for(int chunk_elems) {
   return chunk_elems == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (chunk_elems == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
 }
@@ -113,7 +122,11 @@ struct GatherParams {
   int act;
   float* stats;                  // optional [n][cd][2]: per-(sample, channel) sum / sum of squares of the fp32 pre-activation
   int kstagger;                  // 1: rotate each CTA's K-loop start
+  int tpc;                       // destination tiles per CTA (each with its own TMEM accumulator)
+  uint32_t tmem_cols;            // power of two >= tpc * accumulator stride
 };
+
+constexpr int MAX_TPC = 8;
 
 // Sum each of a lane's 32 values across the 32 lanes of the warp with 31 shuffles: on return a[0] of lane L holds
 // the warp-wide total of original index L (recursive halving: at offset o a lane keeps the half selected by bit o).
@@ -139,7 +152,8 @@ struct GatherCfg {
   static constexpr int STAGES_RAW = (int)((BN == 256 ? 196608u : 98304u) / STAGE_BYTES);
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : (STAGES_RAW < 2 ? 2 : STAGES_RAW);
   static constexpr uint32_t TX_BYTES = BM * BK * 2 + BN * BK * 2;
-  static constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
+  static constexpr uint32_t ACC_COLS = BN < 32 ? 32 : BN;     // TMEM columns of one accumulator
+  static constexpr int TPC_LIMIT = (int)(256u / ACC_COLS) > MAX_TPC ? MAX_TPC : (int)(256u / ACC_COLS);
   static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + 1024 + 256 + (size_t)BN * 2 * sizeof(float);
 };
 
@@ -153,16 +167,16 @@ tc_gather_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint64_t* full_bar = (uint64_t*)(smem + STAGES * Cfg::STAGE_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* tmem_full = empty_bar + STAGES;
-  uint32_t* tmem_slot = (uint32_t*)(tmem_full + 1);
+  uint64_t* tmem_full = empty_bar + STAGES;          // one per accumulator
+  uint32_t* tmem_slot = (uint32_t*)(tmem_full + MAX_TPC);
   float* sstat = (float*)(tmem_slot + 2);          // [BN][2] partial InstanceNorm statistics of this tile
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  int t = blockIdx.x;
-  const int tx = t % P.tiles_x; t /= P.tiles_x;
-  const int ty = t % P.tiles_y;
-  const int tn = t / P.tiles_y;
-  const int x0 = tx * P.tw, y0 = ty * P.th, n0 = tn * P.tn;
+  // this CTA owns the consecutive destination tiles [t_first, t_first + t_count): one K pipeline runs through all
+  // of them while the epilogue warps drain accumulator i during the main loop of tile i + 1
+  const int tiles_total = P.tiles_x * P.tiles_y * P.tiles_n;
+  const int t_first = blockIdx.x * P.tpc;
+  const int t_count = (tiles_total - t_first < P.tpc) ? (tiles_total - t_first) : P.tpc;
   const int c0 = blockIdx.y * BN;
   const int ksteps = P.ntaps * P.kchunks;
 
@@ -170,10 +184,10 @@ tc_gather_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     prefetch_tmap(&tmA);
     prefetch_tmap(&tmB);
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    mbar_init(tmem_full, 1);
+    for (int i = 0; i < MAX_TPC; ++i) mbar_init(&tmem_full[i], 1);
     fence_mbar_init();
   }
-  if (warp == 2) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+  if (warp == 2) tmem_alloc(tmem_slot, P.tmem_cols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -186,15 +200,21 @@ tc_gather_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       // every CTA walks the K loop from a different starting step (the accumulation order is irrelevant): CTAs
       // running concurrently then fetch DIFFERENT weight tiles instead of hammering the same L2 lines
       int kk = P.kstagger ? (int)((blockIdx.x * 5u + blockIdx.y * 3u) % (unsigned)ksteps) : 0;
-      for (int ks = 0; ks < ksteps; ++ks) {
-        const int tap = kk / P.kchunks, kc = kk - tap * P.kchunks;
-        if (++kk == ksteps) kk = 0;
-        mbar_wait(&empty_bar[stage], phase ^ 1);
-        uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
-        mbar_expect_tx(&full_bar[stage], Cfg::TX_BYTES);
-        tma_load_4d(sa, &tmA, &full_bar[stage], kc * BK, x0 * P.sm + P.tdx[tap], y0 * P.sm + P.tdy[tap], n0);
-        tma_load_3d(sa + Cfg::A_BYTES, &tmB, &full_bar[stage], 0, c0, P.twi[tap] * P.kchunks + kc);
-        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      for (int ti = 0; ti < t_count; ++ti) {
+        int t = t_first + ti;
+        const int tx = t % P.tiles_x; t /= P.tiles_x;
+        const int ty = t % P.tiles_y;
+        const int x0 = tx * P.tw, y0 = ty * P.th, n0 = (t / P.tiles_y) * P.tn;
+        for (int ks = 0; ks < ksteps; ++ks) {
+          const int tap = kk / P.kchunks, kc = kk - tap * P.kchunks;
+          if (++kk == ksteps) kk = 0;
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+          mbar_expect_tx(&full_bar[stage], Cfg::TX_BYTES);
+          tma_load_4d(sa, &tmA, &full_bar[stage], kc * BK, x0 * P.sm + P.tdx[tap], y0 * P.sm + P.tdy[tap], n0);
+          tma_load_3d(sa + Cfg::A_BYTES, &tmB, &full_bar[stage], 0, c0, P.twi[tap] * P.kchunks + kc);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
       }
     }
   } else if (warp == 1) {
@@ -203,40 +223,50 @@ tc_gather_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       constexpr uint32_t idesc = make_idesc_bf16(BM, BN, 0, 0);
       constexpr uint32_t SBO = 8 * BK * 2;     // 8 rows of one swizzle atom
       int stage = 0; uint32_t phase = 0;
-      for (int ks = 0; ks < ksteps; ++ks) {
-        mbar_wait(&full_bar[stage], phase);
-        tc_fence_after();
-        const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
-        const uint64_t adesc = make_smem_desc(sa, 16, SBO, layout_for(BK));
-        const uint64_t bdesc = make_smem_desc(sa + Cfg::A_BYTES, 16, SBO, layout_for(BK));
+      for (int ti = 0; ti < t_count; ++ti) {
+        const uint32_t acc = tmem_base + (uint32_t)ti * Cfg::ACC_COLS;
+        for (int ks = 0; ks < ksteps; ++ks) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+          const uint64_t adesc = make_smem_desc(sa, 16, SBO, layout_for(BK));
+          const uint64_t bdesc = make_smem_desc(sa + Cfg::A_BYTES, 16, SBO, layout_for(BK));
 #pragma unroll
-        for (int k = 0; k < BK / 16; ++k)   // +32 bytes per UMMA_K inside the swizzled row
-          umma_bf16(tmem_base, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (ks > 0 || k > 0) ? 1u : 0u);
-        umma_commit(&empty_bar[stage]);
-        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          for (int k = 0; k < BK / 16; ++k)   // +32 bytes per UMMA_K inside the swizzled row
+            umma_bf16(acc, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (ks > 0 || k > 0) ? 1u : 0u);
+          umma_commit(&empty_bar[stage]);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tmem_full[ti]);
       }
-      umma_commit(tmem_full);
     }
   } else {
     // ===== epilogue: warps 2..5; a warp may only touch TMEM lanes 32*(warp%4) .. +31 =====
     const int q = warp & 3;
     const int row = q * 32 + lane;
     const int rx = row % P.tw, ry = (row / P.tw) % P.th, rn = row / (P.tw * P.th);
+    const int et = threadIdx.x - 64;                       // 0..127 within the epilogue warps
+#pragma unroll 1
+    for (int ti = 0; ti < t_count; ++ti) {
+    int t = t_first + ti;
+    const int tx = t % P.tiles_x; t /= P.tiles_x;
+    const int ty = t % P.tiles_y;
+    const int x0 = tx * P.tw, y0 = ty * P.th, n0 = (t / P.tiles_y) * P.tn;
+    const uint32_t acc = tmem_base + (uint32_t)ti * Cfg::ACC_COLS;
     const int px = x0 + rx, py = y0 + ry, pn = n0 + rn;
     const bool valid = px < P.dw && py < P.dh && pn < P.dn;
     const long long off = (long long)pn * P.ds_n + (long long)(py * P.ostep + P.oy0) * P.ds_y +
                           (long long)(px * P.ostep + P.ox0) * P.ds_x + c0;
-    const int et = threadIdx.x - 64;                       // 0..127 within the epilogue warps
     if (P.stats) {
       for (int k = et; k < 2 * BN; k += 128) sstat[k] = 0.f;
       asm volatile("bar.sync 1, 128;" ::: "memory");
     }
-    mbar_wait(tmem_full, 0);
+    mbar_wait(&tmem_full[ti], 0);
     tc_fence_after();
 #pragma unroll 1
-    for (int cc = 0; cc < (int)Cfg::TMEM_COLS; cc += 32) {
+    for (int cc = 0; cc < (int)Cfg::ACC_COLS; cc += 32) {
       float v[32];
-      tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)cc, v);
+      tmem_ld_32x32(acc + ((uint32_t)(q * 32) << 16) + (uint32_t)cc, v);
       if (P.stats) {
         // InstanceNorm statistics in the epilogue: column sums of (acc + bias) and its square over this warp's 32
         // pixels via a transposing butterfly, combined across the four epilogue warps in shared memory
@@ -285,13 +315,15 @@ tc_gather_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       float* gs = P.stats + ((long long)n0 * P.cd + c0) * 2;
       for (int k = et; k < 2 * BN; k += 128)
         if (c0 + (k >> 1) < P.cd) atomicAdd(gs + k, sstat[k]);
+      asm volatile("bar.sync 1, 128;" ::: "memory");       // the next tile zeroes sstat again
     }
+    }   // tiles of this CTA
     tc_fence_before();
   }
   __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    tmem_dealloc(tmem_base, P.tmem_cols);
   }
 }
 
@@ -312,8 +344,24 @@ static int launch_gather_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const
     NEMAR_REQUIRE(e == cudaSuccess, "cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
     attr_set = true;
   }
-  dim3 grid((unsigned)(P.tiles_x * P.tiles_y * P.tiles_n), (unsigned)ctiles);
-  tc_gather_kernel<BN, BK, F32OUT><<<grid, NTHREADS, Cfg::SMEM, s>>>(tmA, tmB, P);
+  // several destination tiles per CTA when the K loop is short (the fixed cost per CTA — launch, barrier and TMEM
+  // set-up, pipeline fill, epilogue — then dominates), as long as the grid still spans >= 4 waves of resident CTAs
+  GatherParams Q = P;
+  const int tiles = P.tiles_x * P.tiles_y * P.tiles_n, ksteps = P.ntaps * P.kchunks;
+  static const int tpc_env = [] { const char* e = getenv("NEMAR_TC_TPC"); return e ? atoi(e) : 0; }();
+  int tpc = 1;
+  static const int ktarget = [] { const char* e = getenv("NEMAR_TC_TPC_K"); return e ? atoi(e) : 64; }();
+  while (tpc * ksteps < ktarget && tpc * 2 <= Cfg::TPC_LIMIT) tpc *= 2;
+  static const int waves = [] { const char* e = getenv("NEMAR_TC_TPC_WAVES"); return e ? atoi(e) : 1; }();
+  while (tpc > 1 && (long long)((tiles + tpc - 1) / tpc) * ctiles < (long long)waves * 2 * sm_count()) tpc >>= 1;
+  if (tpc_env > 0) tpc = tpc_env < Cfg::TPC_LIMIT ? tpc_env : Cfg::TPC_LIMIT;
+  if (tpc < 1) tpc = 1;
+  Q.tpc = tpc;
+  uint32_t cols = 32;
+  while (cols < (uint32_t)tpc * Cfg::ACC_COLS) cols <<= 1;
+  Q.tmem_cols = cols;
+  dim3 grid((unsigned)((tiles + tpc - 1) / tpc), (unsigned)ctiles);
+  tc_gather_kernel<BN, BK, F32OUT><<<grid, NTHREADS, Cfg::SMEM, s>>>(tmA, tmB, Q);
   NEMAR_LAUNCH_CHECK();
   return 0;
 }
@@ -456,18 +504,20 @@ struct WgradParams {
   int m_channels;                 // channels of the M operand (chunks beyond it are neither loaded nor used)
   int shift_on_a;                 // 0: A = dY, B = X (tap-shifted);  1 (swapped roles): A = X (tap-shifted), B = dY
   float* partial;                 // [split][tap][co_tiles*128][ci]
+  int stages;                     // ring depth (<= WG_MAX_STAGES)
+  uint32_t a_bytes, stage_bytes;  // bytes of the M-operand chunks actually loaded per stage / of one whole stage
+  uint32_t bar_offset;            // barriers live behind the ring plus the slack the MMA's unused M rows read into
 };
+
+constexpr int WG_MAX_STAGES = 8;
 
 // CA / CB: channels per TMA chunk of dY / X (64, 32 or 16 -> swizzle 128/64/32 B); BN: input channels per CTA
 template <int CA, int CB, int BN>
 struct WgradCfg {
   static constexpr int NA = BM / CA, NB = BN / CB;
   static constexpr uint32_t CHUNK_A = WG_KP * CA * 2, CHUNK_B = WG_KP * CB * 2;     // >= 2 KB, multiples of 1 KB
-  static constexpr uint32_t A_BYTES = NA * CHUNK_A, B_BYTES = NB * CHUNK_B, STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES_RAW = (int)(180224u / STAGE_BYTES);
-  static constexpr int STAGES = STAGES_RAW > 6 ? 6 : (STAGES_RAW < 2 ? 2 : STAGES_RAW);
+  static constexpr uint32_t B_BYTES = NB * CHUNK_B;
   static constexpr uint32_t TMEM_COLS = BN <= 32 ? 32 : (BN <= 64 ? 64 : (BN <= 128 ? 128 : 256));
-  static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + 1024 + 256;
 };
 
 template <int CA, int CB, int BN>
@@ -475,12 +525,12 @@ __global__ void __launch_bounds__(NTHREADS)
 tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ CUtensorMap tmX,
                 const __grid_constant__ WgradParams P) {
   using Cfg = WgradCfg<CA, CB, BN>;
-  constexpr int STAGES = Cfg::STAGES;
+  const int STAGES = P.stages;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  uint64_t* full_bar = (uint64_t*)(smem + STAGES * Cfg::STAGE_BYTES);
-  uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* tmem_full = empty_bar + STAGES;
+  uint64_t* full_bar = (uint64_t*)(smem + P.bar_offset);
+  uint64_t* empty_bar = full_bar + WG_MAX_STAGES;
+  uint64_t* tmem_full = empty_bar + WG_MAX_STAGES;
   uint32_t* tmem_slot = (uint32_t*)(tmem_full + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -519,8 +569,10 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant_
         const int tn = t / P.tiles_y;
         const int x0 = tx * P.tw, y0 = ty * P.th, n0 = tn * P.tn;
         mbar_wait(&empty_bar[stage], phase ^ 1);
-        uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
-        // channel chunks of the M operand beyond its extent feed accumulator rows nobody reads: skip their loads
+        uint8_t* sa = smem + stage * P.stage_bytes;
+        // channel chunks of the M operand beyond its extent feed accumulator rows nobody reads: their loads are
+        // skipped, and when the whole M operand is narrower than 128 channels the stage does not even reserve room
+        // for them (the MMA then reads those rows from whatever follows — the N operand, the next stage, the slack)
         int na = (P.m_channels - cot * BM + CA - 1) / CA;
         if (na > Cfg::NA) na = Cfg::NA;
         mbar_expect_tx(&full_bar[stage], (uint32_t)na * Cfg::CHUNK_A + Cfg::B_BYTES);
@@ -532,7 +584,7 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant_
           if (c < na) tma_load_4d(sa + c * Cfg::CHUNK_A, &tmDY, &full_bar[stage], cot * BM + c * CA, xa, ya, n0);
 #pragma unroll
         for (int c = 0; c < Cfg::NB; ++c)
-          tma_load_4d(sa + Cfg::A_BYTES + c * Cfg::CHUNK_B, &tmX, &full_bar[stage], cit * BN + c * CB, xb, yb, n0);
+          tma_load_4d(sa + P.a_bytes + c * Cfg::CHUNK_B, &tmX, &full_bar[stage], cit * BN + c * CB, xb, yb, n0);
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
@@ -546,9 +598,9 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant_
       for (int ks = 0; ks < ksteps; ++ks) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
-        const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+        const uint32_t sa = smem_u32(smem + stage * P.stage_bytes);
         const uint64_t adesc = make_smem_desc(sa, Cfg::CHUNK_A, SBO_A, layout_for(CA));
-        const uint64_t bdesc = make_smem_desc(sa + Cfg::A_BYTES, Cfg::CHUNK_B, SBO_B, layout_for(CB));
+        const uint64_t bdesc = make_smem_desc(sa + P.a_bytes, Cfg::CHUNK_B, SBO_B, layout_for(CB));
 #pragma unroll
         for (int k = 0; k < WG_KP / 16; ++k)
           umma_bf16(tmem_base, adesc + (uint64_t)(k * KADV_A), bdesc + (uint64_t)(k * KADV_B), idesc,
@@ -575,9 +627,11 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant_
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = 0.f;
       }
+      if (cot * BM + row < P.m_channels) {     // rows beyond the M operand are never read by the finalize pass
 #pragma unroll
-      for (int j = 0; j < 32; j += 4)
-        if (cc + j < BN) *reinterpret_cast<float4*>(out + cc + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        for (int j = 0; j < 32; j += 4)
+          if (cc + j < BN) *reinterpret_cast<float4*>(out + cc + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+      }
     }
     tc_fence_before();
   }
@@ -610,6 +664,8 @@ __global__ void wgrad_finalize_kernel(const float* __restrict__ partial, float* 
 
 struct WgradPlan {
   int CA, CB, BN, tw, th, tn, tiles_x, tiles_y, tiles_n, splits, tiles_per_split, co_tiles, ci_tiles, taps;
+  int stages, occupancy;
+  uint32_t a_bytes, stage_bytes, bar_offset, smem_bytes;
   int swapped;      // 1: M operand = X (input channels), N operand = dY — for heads with few output channels
   int64_t ws_bytes;
 };
@@ -638,7 +694,34 @@ static bool plan_wgrad(const nemar_tensor* x, const nemar_tensor* dy, int kh, in
   p.ci_tiles = nop->c / p.BN;
   const int total = p.tiles_x * p.tiles_y * p.tiles_n;
   const int base = p.taps * p.co_tiles * p.ci_tiles;
-  int splits = (148 * 2 + base - 1) / base;        // ~2 CTAs per SM in flight
+  // shared-memory ring: only the M chunks that exist are given room when a single tile covers the M operand
+  const int na_full = BM / p.CA;
+  int a_chunks = (mop->c + p.CA - 1) / p.CA;
+  if (p.co_tiles > 1 || a_chunks > na_full) a_chunks = na_full;
+  const uint32_t chunk_a = WG_KP * p.CA * 2, b_bytes = (uint32_t)(p.BN / p.CB) * WG_KP * p.CB * 2;
+  p.a_bytes = a_chunks * chunk_a;
+  p.stage_bytes = p.a_bytes + b_bytes;
+  const uint32_t slack = (na_full - a_chunks) * chunk_a;
+  // residency: as many CTAs per SM (<= 4, TMEM permitting) as still leaves each a ring of >= 4 stages
+  const int tmem_cols = p.BN <= 32 ? 32 : (p.BN <= 64 ? 64 : (p.BN <= 128 ? 128 : 256));
+  static const int occ_env = [] { const char* e = getenv("NEMAR_WG_OCC"); return e ? atoi(e) : 0; }();
+  int occ = 4;
+  for (;; --occ) {
+    const int64_t per = 233472 / occ - 1024 /*reserved per CTA*/ - 1024 /*alignment*/ - 256 - (int64_t)slack;
+    int st = (int)(per / (int64_t)p.stage_bytes);
+    if (st > WG_MAX_STAGES) st = WG_MAX_STAGES;
+    p.stages = st;
+    const bool fits_tmem = occ * tmem_cols <= 512;
+    if (occ == 1 || (fits_tmem && st >= 4 && (occ_env <= 0 || occ <= occ_env))) break;
+  }
+  if (p.stages < 2) return false;
+  p.occupancy = occ;
+  p.bar_offset = (uint32_t)p.stages * p.stage_bytes + slack;
+  p.smem_bytes = p.bar_offset + 1024 + 256;
+  // split K so that the grid is (at most) ONE full wave of resident CTAs: a partial extra wave costs a whole one
+  static const int legacy = [] { const char* e = getenv("NEMAR_WG_LEGACY_SPLITS"); return e ? atoi(e) : 0; }();
+  int splits = legacy ? (148 * 2 + base - 1) / base : (sm_count() * occ) / base;
+  if (!legacy && splits > total / 8) splits = total / 8;     // >= 8 k-steps per CTA
   if (splits > total) splits = total;
   if (splits < 1) splits = 1;
   p.tiles_per_split = (total + splits - 1) / splits;
@@ -649,15 +732,14 @@ static bool plan_wgrad(const nemar_tensor* x, const nemar_tensor* dy, int kh, in
 
 template <int CA, int CB, int BN>
 static int launch_wgrad_t(const CUtensorMap& tmDY, const CUtensorMap& tmX, const WgradParams& P, const WgradPlan& pl, cudaStream_t s) {
-  using Cfg = WgradCfg<CA, CB, BN>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(tc_wgrad_kernel<CA, CB, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
+    cudaError_t e = cudaFuncSetAttribute(tc_wgrad_kernel<CA, CB, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
     NEMAR_REQUIRE(e == cudaSuccess, "cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
     attr_set = true;
   }
   dim3 grid((unsigned)(pl.taps * pl.co_tiles * pl.ci_tiles), (unsigned)pl.splits);
-  tc_wgrad_kernel<CA, CB, BN><<<grid, NTHREADS, Cfg::SMEM, s>>>(tmDY, tmX, P);
+  tc_wgrad_kernel<CA, CB, BN><<<grid, NTHREADS, pl.smem_bytes, s>>>(tmDY, tmX, P);
   NEMAR_LAUNCH_CHECK();
   return 0;
 }
@@ -722,6 +804,7 @@ int tc_wgrad(const nemar_tensor* x_in, const nemar_tensor* dy, float* dw, int co
   P.m_channels = pl.swapped ? x.c : dy->c;
   P.shift_on_a = pl.swapped;
   P.partial = (float*)workspace;
+  P.stages = pl.stages; P.a_bytes = pl.a_bytes; P.stage_bytes = pl.stage_bytes; P.bar_offset = pl.bar_offset;
   if (pl.CA == 64) rc = launch_wgrad_a<64>(tmDY, tmX, P, pl, s);
   else if (pl.CA == 32) rc = launch_wgrad_a<32>(tmDY, tmX, P, pl, s);
   else rc = launch_wgrad_a<16>(tmDY, tmX, P, pl, s);
