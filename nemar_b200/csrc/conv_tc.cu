@@ -122,6 +122,7 @@ struct GatherParams {
   int act;
   float* stats;                  // optional [n][cd][2]: per-(sample, channel) sum / sum of squares of the fp32 pre-activation
   int kstagger;                  // 1: rotate each CTA's K-loop start
+  int stages;                    // ring depth (<= GatherCfg::STAGES)
   int tpc;                       // destination tiles per CTA (each with its own TMEM accumulator)
   uint32_t tmem_cols;            // power of two >= tpc * accumulator stride
 };
@@ -153,7 +154,6 @@ struct GatherCfg {
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : (STAGES_RAW < 2 ? 2 : STAGES_RAW);
   static constexpr uint32_t TX_BYTES = BM * BK * 2 + BN * BK * 2;
   static constexpr uint32_t ACC_COLS = BN < 32 ? 32 : BN;     // TMEM columns of one accumulator
-  static constexpr int TPC_LIMIT = (int)(256u / ACC_COLS) > MAX_TPC ? MAX_TPC : (int)(256u / ACC_COLS);
   static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + 1024 + 256 + (size_t)BN * 2 * sizeof(float);
 };
 
@@ -162,12 +162,12 @@ __global__ void __launch_bounds__(NTHREADS)
 tc_gather_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ GatherParams P) {
   using Cfg = GatherCfg<BN, BK>;
-  constexpr int STAGES = Cfg::STAGES;
+  const int STAGES = P.stages;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint64_t* full_bar = (uint64_t*)(smem + STAGES * Cfg::STAGE_BYTES);
-  uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* tmem_full = empty_bar + STAGES;          // one per accumulator
+  uint64_t* empty_bar = full_bar + Cfg::STAGES;
+  uint64_t* tmem_full = empty_bar + Cfg::STAGES;     // one per accumulator
   uint32_t* tmem_slot = (uint32_t*)(tmem_full + MAX_TPC);
   float* sstat = (float*)(tmem_slot + 2);          // [BN][2] partial InstanceNorm statistics of this tile
 
@@ -327,12 +327,31 @@ tc_gather_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   }
 }
 
-static void pick_tile(int dw, int dh, int& tw, int& th, int& tn, int total) {
-  tw = 1;
-  while (tw < dw && tw < total) tw <<= 1;
-  th = 1;
-  while (th < dh && tw * th < total) th <<= 1;
-  tn = total / (tw * th);
+// Pixel box (tw x th x tn, all powers of two, product `total`) that wastes the fewest accumulator rows on the
+// (dw x dh x dn) index space: e.g. the 66x66 reflect-padded maps of the ResnetBlock dgrad fill only 52 % of 128x1
+// boxes but 94 % of 4x4x8 ones.  Narrow boxes cost a little TMA efficiency, hence the small penalty below 8 pixels.
+static void pick_tile(int dw, int dh, int dn, int& tw, int& th, int& tn, int total, bool one_sample = false) {
+  static const int legacy = [] { const char* e = getenv("NEMAR_TC_LEGACY_TILES"); return e ? atoi(e) : 0; }();
+  if (legacy) {
+    tw = 1;
+    while (tw < dw && tw < total) tw <<= 1;
+    th = 1;
+    while (th < dh && tw * th < total) th <<= 1;
+    tn = total / (tw * th);
+    return;
+  }
+  double best = 1e300;
+  tw = total; th = 1; tn = 1;
+  for (int a = total; a >= 1; a >>= 1)
+    for (int b = total / a; b >= 1; b >>= 1) {
+      const int c = total / (a * b);
+      if (one_sample && c != 1) continue;
+      const double padded = (double)((dw + a - 1) / a * a) * ((dh + b - 1) / b * b) * ((dn + c - 1) / c * c);
+      double pen = 1.0;
+      for (int q = a; q < 8; q <<= 1) pen += 0.02;
+      const double cost = padded * pen;
+      if (cost < best * (1.0 - 1e-9)) { best = cost; tw = a; th = b; tn = c; }   // ties keep the widest box
+    }
 }
 
 template <int BN, int BK, bool F32OUT>
@@ -348,20 +367,36 @@ static int launch_gather_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const
   // set-up, pipeline fill, epilogue — then dominates), as long as the grid still spans >= 4 waves of resident CTAs
   GatherParams Q = P;
   const int tiles = P.tiles_x * P.tiles_y * P.tiles_n, ksteps = P.ntaps * P.kchunks;
+  // ring depth: the default fills ~96 KB (two CTAs per SM); NEMAR_TC_RING_KB trades depth for residency
+  static const int ring_kb = [] { const char* e = getenv("NEMAR_TC_RING_KB"); return e ? atoi(e) : 0; }();
+  int stages = Cfg::STAGES;
+  if (ring_kb > 0 && BN != 256) {
+    stages = (int)((uint32_t)ring_kb * 1024u / Cfg::STAGE_BYTES);
+    if (stages > Cfg::STAGES) stages = Cfg::STAGES;
+    if (stages < 2) stages = 2;
+  }
+  Q.stages = stages;
+  const size_t smem_bytes = Cfg::SMEM - (size_t)(Cfg::STAGES - stages) * Cfg::STAGE_BYTES;
+  int occ = (int)(233472 / (smem_bytes + 1024));
+  if (occ < 1) occ = 1;
+  if (occ > 8) occ = 8;
+  int tpc_limit = (int)((512u / (uint32_t)occ) / Cfg::ACC_COLS);     // TMEM columns shared by the resident CTAs
+  if (tpc_limit > MAX_TPC) tpc_limit = MAX_TPC;
+  if (tpc_limit < 1) tpc_limit = 1;
   static const int tpc_env = [] { const char* e = getenv("NEMAR_TC_TPC"); return e ? atoi(e) : 0; }();
   int tpc = 1;
   static const int ktarget = [] { const char* e = getenv("NEMAR_TC_TPC_K"); return e ? atoi(e) : 64; }();
-  while (tpc * ksteps < ktarget && tpc * 2 <= Cfg::TPC_LIMIT) tpc *= 2;
+  while (tpc * ksteps < ktarget && tpc * 2 <= tpc_limit) tpc *= 2;
   static const int waves = [] { const char* e = getenv("NEMAR_TC_TPC_WAVES"); return e ? atoi(e) : 1; }();
-  while (tpc > 1 && (long long)((tiles + tpc - 1) / tpc) * ctiles < (long long)waves * 2 * sm_count()) tpc >>= 1;
-  if (tpc_env > 0) tpc = tpc_env < Cfg::TPC_LIMIT ? tpc_env : Cfg::TPC_LIMIT;
+  while (tpc > 1 && (long long)((tiles + tpc - 1) / tpc) * ctiles < (long long)waves * occ * sm_count()) tpc >>= 1;
+  if (tpc_env > 0) tpc = tpc_env < tpc_limit ? tpc_env : tpc_limit;
   if (tpc < 1) tpc = 1;
   Q.tpc = tpc;
   uint32_t cols = 32;
   while (cols < (uint32_t)tpc * Cfg::ACC_COLS) cols <<= 1;
   Q.tmem_cols = cols;
   dim3 grid((unsigned)((tiles + tpc - 1) / tpc), (unsigned)ctiles);
-  tc_gather_kernel<BN, BK, F32OUT><<<grid, NTHREADS, Cfg::SMEM, s>>>(tmA, tmB, Q);
+  tc_gather_kernel<BN, BK, F32OUT><<<grid, NTHREADS, smem_bytes, s>>>(tmA, tmB, Q);
   NEMAR_LAUNCH_CHECK();
   return 0;
 }
@@ -447,7 +482,8 @@ int tc_gather_gemm(const nemar_tensor* src_in, const nemar_tensor* dst_in, const
     NEMAR_REQUIRE(P.ntaps > 0, "tc_gather_gemm: parity class without taps");
     P.kchunks = src.c / BK;
     P.cs = src.c;
-    pick_tile(P.dw, P.dh, P.tw, P.th, P.tn, BM);
+    static const int fuse_env = [] { const char* e = getenv("NEMAR_FUSED_STATS"); return e ? atoi(e) : 0; }();
+    pick_tile(P.dw, P.dh, P.dn, P.tw, P.th, P.tn, BM, fuse_env && stats);
     P.tiles_x = (P.dw + P.tw - 1) / P.tw;
     P.tiles_y = (P.dh + P.th - 1) / P.th;
     P.tiles_n = (P.dn + P.tn - 1) / P.tn;
@@ -685,7 +721,7 @@ static bool plan_wgrad(const nemar_tensor* x, const nemar_tensor* dy, int kh, in
   const nemar_tensor* nop = p.swapped ? dy : x;      // N operand
   if (!wgrad_bn(nop->c, p.CB, p.BN)) return false;
   p.CA = chunk_for(mop->c);
-  pick_tile(dy->w, dy->h, p.tw, p.th, p.tn, WG_KP);
+  pick_tile(dy->w, dy->h, dy->n, p.tw, p.th, p.tn, WG_KP);
   p.tiles_x = (dy->w + p.tw - 1) / p.tw;
   p.tiles_y = (dy->h + p.th - 1) / p.th;
   p.tiles_n = (dy->n + p.tn - 1) / p.tn;
@@ -705,14 +741,16 @@ static bool plan_wgrad(const nemar_tensor* x, const nemar_tensor* dy, int kh, in
   // residency: as many CTAs per SM (<= 4, TMEM permitting) as still leaves each a ring of >= 4 stages
   const int tmem_cols = p.BN <= 32 ? 32 : (p.BN <= 64 ? 64 : (p.BN <= 128 ? 128 : 256));
   static const int occ_env = [] { const char* e = getenv("NEMAR_WG_OCC"); return e ? atoi(e) : 0; }();
-  int occ = 4;
+  static const int occ_max = [] { const char* e = getenv("NEMAR_WG_OCC_MAX"); return e ? atoi(e) : 4; }();
+  static const int min_stages = [] { const char* e = getenv("NEMAR_WG_MIN_STAGES"); return e ? atoi(e) : 4; }();
+  int occ = occ_max < 1 ? 1 : (occ_max > 8 ? 8 : occ_max);
   for (;; --occ) {
     const int64_t per = 233472 / occ - 1024 /*reserved per CTA*/ - 1024 /*alignment*/ - 256 - (int64_t)slack;
     int st = (int)(per / (int64_t)p.stage_bytes);
     if (st > WG_MAX_STAGES) st = WG_MAX_STAGES;
     p.stages = st;
     const bool fits_tmem = occ * tmem_cols <= 512;
-    if (occ == 1 || (fits_tmem && st >= 4 && (occ_env <= 0 || occ <= occ_env))) break;
+    if (occ == 1 || (fits_tmem && st >= min_stages && (occ_env <= 0 || occ <= occ_env))) break;
   }
   if (p.stages < 2) return false;
   p.occupancy = occ;
