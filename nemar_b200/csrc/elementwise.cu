@@ -7,6 +7,7 @@
 #include "common.cuh"
 #include "vec.cuh"
 #include "norm_fast.cuh"
+#include "norm_lean.cuh"
 #include <cstdlib>
 
 static bool norm_fast_enabled() {
@@ -447,6 +448,16 @@ static int launch_plane_reduce(const nemar_tensor* xt, const float* stats, int a
   const int64_t hw = (int64_t)x.h * x.w;
   // measured (C2, ms/step, generic -> fast): backward reduce 5.80 -> 4.37; statistics 14.38 -> 14.89 (inside fprop),
   // forward 2.71 -> 2.82, backward apply 6.96 -> 7.32 — so only the backward reduction takes the fast path
+  if ((nlean::enabled_mask() & (MODE == 0 ? 2 : 4)) && nfast::eligible(xt) && (!dyt || nfast::eligible(dyt))) {
+    dim3 grid(nlean::chunks_for(hw, x.c / 8, x.n, true), x.n);
+    if (MODE == 0) {
+      nlean::reduce_kernel<MODE, 2, NEMAR_ACT_NONE><<<grid, 256, sizeof(float) * 4 * x.c, s>>>(x, stats, act, dy, pad_mode, inv_hw, out);
+    } else {
+      NLEAN_ACT_SWITCH(act, (nlean::reduce_kernel<MODE, 2, A><<<grid, 256, sizeof(float) * 4 * x.c, s>>>(x, stats, act, dy, pad_mode, inv_hw, out)));
+    }
+    NEMAR_LAUNCH_CHECK();
+    return 0;
+  }
   if (MODE == 1 && norm_fast_enabled() && nfast::eligible(xt) && (!dyt || nfast::eligible(dyt))) {
     const int G = x.c / 8;
     dim3 grid(nfast::chunks_for(hw, G, x.n), x.n);
@@ -620,6 +631,12 @@ NEMAR_API int nemar_norm_act_fwd(const nemar_tensor* x, const float* stats, int 
   TView xv = make_view(x), yv = make_view(y), rv = residual ? make_view(residual) : xv;
   const float inv_hw = 1.f / ((float)xv.h * (float)xv.w);
   cudaStream_t s = (cudaStream_t)stream;
+  if ((nlean::enabled_mask() & 1) && nfast::eligible(x) && nfast::eligible(y) && (!residual || nfast::eligible(residual))) {
+    dim3 grid(nlean::chunks_for((int64_t)yv.hp * yv.wp, yv.c / 8, yv.n), yv.n);
+    NLEAN_ACT_SWITCH(act, (nlean::fwd_kernel<A><<<grid, 256, sizeof(float) * 2 * yv.c, s>>>(xv, stats, act, rv, residual != nullptr, yv, pad_mode, inv_hw)));
+    NEMAR_LAUNCH_CHECK();
+    return 0;
+  }
   static const bool fast_fwd = [] { const char* e = getenv("NEMAR_NORM_FAST_ALL"); return e && atoi(e); }();
   if (fast_fwd && nfast::eligible(x) && nfast::eligible(y) && (!residual || nfast::eligible(residual))) {
     dim3 grid(nfast::chunks_for((int64_t)yv.hp * yv.wp, yv.c / 8, yv.n), yv.n);
@@ -748,6 +765,14 @@ NEMAR_API int nemar_norm_act_bwd_apply(const nemar_tensor* x, const float* stats
   TView xv = make_view(x), dyv = make_view(dy), dxv = make_view(dx), dr = dres ? make_view(dres) : xv;
   const float inv_hw = 1.f / ((float)xv.h * (float)xv.w);
   cudaStream_t s = (cudaStream_t)stream;
+  if ((nlean::enabled_mask() & 8) && nfast::eligible(x) && nfast::eligible(dy) && nfast::eligible(dx) && (!dres || nfast::eligible(dres))) {
+    if (db) cudaMemsetAsync(db, 0, sizeof(float) * xv.c, s);
+    dim3 grid(nlean::chunks_for((int64_t)xv.h * xv.w, xv.c / 8, xv.n, false, true), xv.n);
+    NLEAN_ACT_SWITCH(act, (nlean::bwd_apply_kernel<A><<<grid, 256, sizeof(float) * 5 * xv.c, s>>>(
+        xv, stats, act, dyv, pad_mode, red, dxv, dr, dres != nullptr, dres_accumulate, inv_hw, db)));
+    NEMAR_LAUNCH_CHECK();
+    return 0;
+  }
   static const bool fast_apply = [] { const char* e = getenv("NEMAR_NORM_FAST_ALL"); return e && atoi(e); }();
   if (fast_apply && nfast::eligible(x) && nfast::eligible(dy) && nfast::eligible(dx) && (!dres || nfast::eligible(dres))) {
     if (db) cudaMemsetAsync(db, 0, sizeof(float) * xv.c, s);

@@ -154,7 +154,9 @@ def call(name, *args):
                 _call(name, *args)
                 return
         else:
-            key, geo, flops = name.replace("nemar_", ""), name, 0.0
+            key, flops = name.replace("nemar_", ""), 0.0
+            t0 = next((a for a in args if isinstance(a, NemarTensor)), None)
+            geo = key if t0 is None else "%s n%d c%d @%dx%d" % (key, t0.n, t0.c, t0.h, t0.w)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         _call(name, *args)
