@@ -55,6 +55,11 @@ const char* nemar_last_error(void);
 int nemar_version(void);
 /* 1 when the tcgen05/TMA implicit-GEMM path can take this geometry+dtype, else 0 (generic path). */
 int nemar_conv2d_tc_supported(const nemar_conv_geom* g, int dtype, int h_in, int w_in);
+/* Engine tuning switch (process-wide; not a semantic option — results stay within the same tolerance).
+ *   "pair": 1 = destinations of k*256 channels run on CTA pairs (tcgen05 cta_group::2, 256x256 tiles), 0 = single-CTA
+ *   tiles.  value < 0 only queries.  Returns the previous value, or -1 for an unknown key.  Initial value:
+ *   environment NEMAR_TC_PAIR. */
+int nemar_conv2d_set_option(const char* key, int value);
 
 /* ---------------------------------------------------------------------------------------------
  * Layout crossings at the reference-facing module boundary (NCHW fp32 images <-> engine NHWC).

@@ -132,3 +132,5 @@ NEMAR_API int nemar_conv2d_tc_supported(const nemar_conv_geom* g, int dtype, int
   if (!(g->stride == 1 || g->stride == 2) || g->kh * g->kw > 49) return 0;
   return 1;   // any channel count: the host pads activations/weights to a multiple of 16
 }
+
+NEMAR_API int nemar_conv2d_set_option(const char* key, int value) { return tc_set_option(key, value); }

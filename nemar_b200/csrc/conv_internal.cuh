@@ -35,6 +35,7 @@ int generic_pack(const float* w, void* out, int dtype, int O, int op, int I, int
 
 // tcgen05 / TMA engine — conv_tc.cu
 bool tc_engine_built();
+int tc_set_option(const char* key, int value);   // -> previous value, -1: unknown key
 bool tc_gather_supported(const nemar_tensor* src, const nemar_tensor* dst, int wp_cs, const GatherGeom& gg);
 int tc_gather_gemm(const nemar_tensor* src, const nemar_tensor* dst, const void* wp, int wp_cs,
                    const float* bias, int act, float* stats, const GatherGeom& gg, cudaStream_t s);

@@ -25,6 +25,7 @@
 #include "tc_common.cuh"
 
 #include <cstdlib>
+#include <cstring>
 #include <mutex>
 
 using namespace tc;
@@ -327,6 +328,154 @@ tc_gather_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   }
 }
 
+// -------------------------------------------------------------------------------------------------
+// gather kernel, CTA-pair variant (cta_group::2): destination tiles of 256 pixels x 256 channels per pair
+// -------------------------------------------------------------------------------------------------
+// The single-CTA kernel fetches 32 KB (A 128x64 + B 128x64) per 128x128x64 MMA step and is bound by the chip-wide
+// L2 -> SM TMA throughput (~6.3 KB/clk), not by the tensor pipe.  Here two CTAs of a cluster (the two SMs of a TPC)
+// run ONE M=256 x N=256 MMA per k-step: each CTA stages its own 128 pixels of A and its own 128 of the 256 weight
+// rows, i.e. 32 KB per 128x256x64 of work per CTA — twice the flops per fetched byte.  Protocol:
+//   * both producers issue TMA into their own ring; every byte is counted on the LEADER's full barrier (armed by
+//     the leader with the bytes of both CTAs);
+//   * the leader's elected thread issues tcgen05.mma.cta_group::2 (reads both CTAs' shared memory at the same
+//     offsets, writes 128 accumulator lanes into each CTA's TMEM) and releases the slot in BOTH CTAs with a
+//     multicast tcgen05.commit; the last commit of a tile publishes the accumulator to both epilogues;
+//   * each CTA's epilogue warps drain their own 128 pixels x 256 channels.
+constexpr int PAIR_BN = 256, PAIR_BK = 64, PAIR_MAX_STAGES = 6, PAIR_MAX_TPC = 2;
+constexpr uint32_t PAIR_A_BYTES = BM * PAIR_BK * 2, PAIR_B_BYTES = (PAIR_BN / 2) * PAIR_BK * 2;
+constexpr uint32_t PAIR_STAGE_BYTES = PAIR_A_BYTES + PAIR_B_BYTES;
+static size_t pair_smem_bytes(int stages) { return (size_t)stages * PAIR_STAGE_BYTES + 1024 + 256; }
+
+__global__ void __launch_bounds__(NTHREADS)
+tc_gather_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                      const __grid_constant__ GatherParams P) {
+  const int STAGES = P.stages;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_bar = (uint64_t*)(smem + STAGES * PAIR_STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + PAIR_MAX_STAGES;
+  uint64_t* tmem_full = empty_bar + PAIR_MAX_STAGES;     // one per accumulator
+  uint32_t* tmem_slot = (uint32_t*)(tmem_full + PAIR_MAX_TPC);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();               // 0 = leader (cluster = blocks 2p, 2p+1 along x)
+  // the pair owns the consecutive tile pairs [p_first, p_first + p_count); tile pair j = tiles 2j (leader), 2j+1
+  const int tiles_total = P.tiles_x * P.tiles_y * P.tiles_n;
+  const int pairs_total = (tiles_total + 1) >> 1;
+  const int p_first = (int)(blockIdx.x >> 1) * P.tpc;
+  const int p_count = (pairs_total - p_first < P.tpc) ? (pairs_total - p_first) : P.tpc;
+  const int c0 = blockIdx.y * PAIR_BN;
+  const int ksteps = P.ntaps * P.kchunks;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmA);
+    prefetch_tmap(&tmB);
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int i = 0; i < PAIR_MAX_TPC; ++i) mbar_init(&tmem_full[i], 1);
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc_pair(tmem_slot, P.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();          // the peer's barriers are initialised before anything of ours can signal them
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== TMA producer (both CTAs) =====
+      const uint32_t full_leader = mapa_u32(smem_u32(&full_bar[0]), 0);
+      int stage = 0; uint32_t phase = 0;
+      for (int ti = 0; ti < p_count; ++ti) {
+        int t = (p_first + ti) * 2 + (int)rank;      // t == tiles_total (odd count): every row out of bounds -> zeros
+        const int tx = t % P.tiles_x; t /= P.tiles_x;
+        const int ty = t % P.tiles_y;
+        const int x0 = tx * P.tw, y0 = ty * P.th, n0 = (t / P.tiles_y) * P.tn;
+        for (int ks = 0; ks < ksteps; ++ks) {
+          const int tap = ks / P.kchunks, kc = ks - tap * P.kchunks;
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * PAIR_STAGE_BYTES;
+          if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * PAIR_STAGE_BYTES);
+          const uint32_t fb = full_leader + (uint32_t)stage * 8u;
+          tma_load_4d_pair(sa, &tmA, fb, kc * PAIR_BK, x0 * P.sm + P.tdx[tap], y0 * P.sm + P.tdy[tap], n0);
+          tma_load_3d_pair(sa + PAIR_A_BYTES, &tmB, fb, 0, c0 + (int)rank * (PAIR_BN / 2), P.twi[tap] * P.kchunks + kc);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && rank == 0) {
+      // ===== MMA issuer (leader CTA only) =====
+      constexpr uint32_t idesc = make_idesc_bf16(2 * BM, PAIR_BN, 0, 0);
+      constexpr uint32_t SBO = 8 * PAIR_BK * 2;
+      int stage = 0; uint32_t phase = 0;
+      for (int ti = 0; ti < p_count; ++ti) {
+        const uint32_t acc = tmem_base + (uint32_t)ti * PAIR_BN;
+        for (int ks = 0; ks < ksteps; ++ks) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * PAIR_STAGE_BYTES);
+          const uint64_t adesc = make_smem_desc(sa, 16, SBO, LAYOUT_SW128);
+          const uint64_t bdesc = make_smem_desc(sa + PAIR_A_BYTES, 16, SBO, LAYOUT_SW128);
+#pragma unroll
+          for (int k = 0; k < PAIR_BK / 16; ++k)
+            umma_bf16_pair(acc, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (ks > 0 || k > 0) ? 1u : 0u);
+          umma_commit_pair(&empty_bar[stage], 3);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit_pair(&tmem_full[ti], 3);
+      }
+    }
+  } else {
+    // ===== epilogue (both CTAs): warps 2..5, TMEM lanes 32*(warp%4) .. +31 of this CTA's 128 pixels =====
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int rx = row % P.tw, ry = (row / P.tw) % P.th, rn = row / (P.tw * P.th);
+#pragma unroll 1
+    for (int ti = 0; ti < p_count; ++ti) {
+      int t = (p_first + ti) * 2 + (int)rank;
+      const int tx = t % P.tiles_x; t /= P.tiles_x;
+      const int ty = t % P.tiles_y;
+      const int x0 = tx * P.tw, y0 = ty * P.th, n0 = (t / P.tiles_y) * P.tn;
+      const uint32_t acc = tmem_base + (uint32_t)ti * PAIR_BN;
+      const int px = x0 + rx, py = y0 + ry, pn = n0 + rn;
+      const bool valid = px < P.dw && py < P.dh && pn < P.dn;
+      const long long off = (long long)pn * P.ds_n + (long long)(py * P.ostep + P.oy0) * P.ds_y +
+                            (long long)(px * P.ostep + P.ox0) * P.ds_x + c0;
+      mbar_wait(&tmem_full[ti], 0);
+      tc_fence_after();
+#pragma unroll 1
+      for (int cc = 0; cc < PAIR_BN; cc += 32) {
+        float v[32];
+        tmem_ld_32x32(acc + ((uint32_t)(q * 32) << 16) + (uint32_t)cc, v);
+        if (valid) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            float f[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float b = P.bias ? __ldg(P.bias + c0 + cc + g * 8 + j) : 0.f;
+              f[j] = act_fwd(v[g * 8 + j] + b, P.act);
+            }
+            uint4 pk;
+            __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&pk);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) h[j] = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+            *reinterpret_cast<uint4*>((__nv_bfloat16*)P.dst + off + cc + g * 8) = pk;
+          }
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  cluster_sync_all();          // neither CTA may leave (or free TMEM) while the pair's MMAs / commits can still touch it
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc_pair(tmem_base, P.tmem_cols);
+  }
+}
+
 // Pixel box (tw x th x tn, all powers of two, product `total`) that wastes the fewest accumulator rows on the
 // (dw x dh x dn) index space: e.g. the 66x66 reflect-padded maps of the ResnetBlock dgrad fill only 52 % of 128x1
 // boxes but 94 % of 4x4x8 ones.  Narrow boxes cost a little TMA efficiency, hence the small penalty below 8 pixels.
@@ -413,6 +562,50 @@ static int launch_gather_k(const CUtensorMap& a, const CUtensorMap& b, const Gat
   return launch_gather_f<BN, 16>(a, b, P, ct, f32, s);
 }
 
+// CTA-pair launch: clusters of 2 along x; grid.x = 2 * ceil(tile pairs / tpc)
+static int launch_gather_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const GatherParams& P, int ctiles, cudaStream_t s) {
+  static const int stages_env = [] { const char* e = getenv("NEMAR_TC_PAIR_STAGES"); return e ? atoi(e) : 3; }();
+  static const int tpc_env = [] { const char* e = getenv("NEMAR_TC_PAIR_TPC"); return e ? atoi(e) : 1; }();
+  int stages = stages_env < 2 ? 2 : (stages_env > PAIR_MAX_STAGES ? PAIR_MAX_STAGES : stages_env);
+  const size_t smem_bytes = pair_smem_bytes(stages);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(tc_gather_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)pair_smem_bytes(PAIR_MAX_STAGES));
+    NEMAR_REQUIRE(e == cudaSuccess, "cudaFuncSetAttribute(pair) failed: %s", cudaGetErrorString(e));
+    attr_set = true;
+  }
+  GatherParams Q = P;
+  Q.stages = stages;
+  const int occ = (int)(233472 / (smem_bytes + 1024)) < 1 ? 1 : (int)(233472 / (smem_bytes + 1024));
+  int tpc = tpc_env < 1 ? 1 : (tpc_env > PAIR_MAX_TPC ? PAIR_MAX_TPC : tpc_env);
+  if (occ * tpc * PAIR_BN > 512) tpc = 1;               // TMEM columns shared by the CTAs resident on one SM
+  Q.tpc = tpc;
+  Q.tmem_cols = (uint32_t)tpc * PAIR_BN;                // 256 or 512: powers of two
+  Q.stats = nullptr; Q.kstagger = 0;
+  const int tiles = P.tiles_x * P.tiles_y * P.tiles_n, pairs = (tiles + 1) / 2;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(2 * ((pairs + tpc - 1) / tpc)), (unsigned)ctiles, 1);
+  cfg.blockDim = dim3(NTHREADS, 1, 1);
+  cfg.dynamicSmemBytes = smem_bytes;
+  cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, tc_gather_pair_kernel, tmA, tmB, Q);
+  NEMAR_REQUIRE(e == cudaSuccess, "tc_gather_pair_kernel launch failed: %s", cudaGetErrorString(e));
+  NEMAR_LAUNCH_CHECK();
+  return 0;
+}
+
+// 0: single-CTA tiles everywhere; 1: CTA pairs (cta_group::2, 256x256 tiles) for destinations of k*256 channels
+static int g_pair_mode = -1;
+static int pair_mode() {
+  if (g_pair_mode < 0) { const char* e = getenv("NEMAR_TC_PAIR"); g_pair_mode = e ? atoi(e) : 0; }
+  return g_pair_mode;
+}
+
 static bool tc_view_ok(const nemar_tensor* t, bool allow_f32) {
   const bool dt_ok = t->dtype == NEMAR_BF16 || (allow_f32 && t->dtype == NEMAR_F32);
   return dt_ok && t->c % 16 == 0 && t->cs % 8 == 0 && t->coff % 8 == 0 && ((((uintptr_t)t->ptr) & 15) == 0);
@@ -427,6 +620,11 @@ static int gather_bn(int cd, int bk, bool f32) {
 }  // namespace
 
 bool tc_engine_built() { return true; }
+
+int tc_set_option(const char* key, int value) {
+  if (key && !strcmp(key, "pair")) { const int old = pair_mode(); if (value >= 0) g_pair_mode = value ? 1 : 0; return old; }
+  return -1;
+}
 
 bool tc_gather_supported(const nemar_tensor* src, const nemar_tensor* dst, int wp_cs, const GatherGeom& gg) {
   if (!tc_view_ok(src, false) || !tc_view_ok(dst, true)) return false;
@@ -447,7 +645,8 @@ int tc_gather_gemm(const nemar_tensor* src_in, const nemar_tensor* dst_in, const
   dst.h += 2 * dst.pad; dst.w += 2 * dst.pad; dst.pad = 0;
   const int BK = chunk_for(src.c);
   const bool f32 = dst.dtype == NEMAR_F32;
-  const int BN = gather_bn(dst.c, BK, f32);
+  const bool pair = pair_mode() > 0 && dst.c % PAIR_BN == 0 && BK == PAIR_BK && !f32;
+  const int BN = pair ? PAIR_BN / 2 : gather_bn(dst.c, BK, f32);     // pair: TMA box = one CTA's half of the weight rows
   const int esz = f32 ? 4 : 2;
   const int taps_total = gg.kh * gg.kw;
   CUtensorMap tmB;
@@ -505,7 +704,12 @@ int tc_gather_gemm(const nemar_tensor* src_in, const nemar_tensor* dst_in, const
     CUtensorMap tmA;
     rc = make_act_map(&tmA, &src, BK, P.tw, P.th, P.tn, gg.sm);
     if (rc) return rc;
-    const int ctiles = (dst.c + BN - 1) / BN;
+    const int ctiles = pair ? dst.c / PAIR_BN : (dst.c + BN - 1) / BN;
+    if (pair) {
+      rc = launch_gather_pair(tmA, tmB, P, ctiles, s);
+      if (rc) return rc;
+      continue;
+    }
     switch (BN) {
       case 256: rc = launch_gather_t<256, 64, false>(tmA, tmB, P, ctiles, s); break;
       case 128: rc = launch_gather_k<128>(tmA, tmB, P, ctiles, BK, f32, s); break;
@@ -678,6 +882,131 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant_
   }
 }
 
+// -------------------------------------------------------------------------------------------------
+// weight gradient, CTA-pair variant (cta_group::2): M = 256 output channels x N = 256 input channels per pair
+// -------------------------------------------------------------------------------------------------
+// The single-CTA kernel stages dY[64 px][128 co] + X[64 px][256 ci] = 48 KB per 128x256x64 step.  A pair stages, per
+// CTA, its own 128 output channels of dY and its own 128 of the 256 input channels of X (32 KB) for the same
+// amount of MMA work per CTA: 1.5x the flops per fetched byte.  Same barrier protocol as tc_gather_pair_kernel.
+constexpr uint32_t WGP_CHUNK = WG_KP * 64 * 2;                 // one 64-channel x 64-pixel TMA box (8 KB)
+constexpr uint32_t WGP_A_BYTES = 2 * WGP_CHUNK, WGP_B_BYTES = 2 * WGP_CHUNK, WGP_STAGE_BYTES = WGP_A_BYTES + WGP_B_BYTES;
+constexpr int WGP_MAX_STAGES = 6;
+static size_t wgrad_pair_smem_bytes(int stages) { return (size_t)stages * WGP_STAGE_BYTES + 1024 + 256; }
+
+__global__ void __launch_bounds__(NTHREADS)
+tc_wgrad_pair_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ CUtensorMap tmX,
+                     const __grid_constant__ WgradParams P) {
+  const int STAGES = P.stages;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_bar = (uint64_t*)(smem + STAGES * WGP_STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + WGP_MAX_STAGES;
+  uint64_t* tmem_full = empty_bar + WGP_MAX_STAGES;
+  uint32_t* tmem_slot = (uint32_t*)(tmem_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  // blockIdx.x = ((tap * co_pairs + co_pair) * ci_tiles + cit) * 2 + rank ; P.co_tiles counts 128-channel tiles
+  int b = (int)(blockIdx.x >> 1);
+  const int cit = b % P.ci_tiles; b /= P.ci_tiles;
+  const int co_pairs = P.co_tiles >> 1;
+  const int cop = b % co_pairs;
+  const int tap = b / co_pairs;
+  const int cot = cop * 2 + (int)rank;          // this CTA's 128-channel tile of dY
+  const int split = blockIdx.y;
+  const int ta = tap / P.kw, tb = tap % P.kw;
+  const int total_tiles = P.tiles_x * P.tiles_y * P.tiles_n;
+  const int t_lo = split * P.tiles_per_split;
+  int t_hi = t_lo + P.tiles_per_split;
+  if (t_hi > total_tiles) t_hi = total_tiles;
+  const int ksteps = t_hi - t_lo;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmDY);
+    prefetch_tmap(&tmX);
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    mbar_init(tmem_full, 1);
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc_pair(tmem_slot, 256);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const uint32_t full_leader = mapa_u32(smem_u32(&full_bar[0]), 0);
+      int stage = 0; uint32_t phase = 0;
+      for (int ks = 0; ks < ksteps; ++ks) {
+        int t = t_lo + ks;
+        const int tx = t % P.tiles_x; t /= P.tiles_x;
+        const int ty = t % P.tiles_y;
+        const int tn = t / P.tiles_y;
+        const int x0 = tx * P.tw, y0 = ty * P.th, n0 = tn * P.tn;
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        uint8_t* sa = smem + stage * WGP_STAGE_BYTES;
+        if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * WGP_STAGE_BYTES);
+        const uint32_t fb = full_leader + (uint32_t)stage * 8u;
+        const int xs = x0 * P.stride - P.pe + tb, ys = y0 * P.stride - P.pe + ta;   // tap-shifted box of X
+#pragma unroll
+        for (int c = 0; c < 2; ++c) tma_load_4d_pair(sa + c * WGP_CHUNK, &tmDY, fb, cot * BM + c * 64, x0, y0, n0);
+#pragma unroll
+        for (int c = 0; c < 2; ++c)
+          tma_load_4d_pair(sa + WGP_A_BYTES + c * WGP_CHUNK, &tmX, fb, cit * 256 + (int)rank * 128 + c * 64, xs, ys, n0);
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && rank == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(2 * BM, 256, 1, 1);
+      constexpr uint32_t SBO = 8 * 64 * 2, KADV = (16 * 64 * 2) >> 4;
+      int stage = 0; uint32_t phase = 0;
+      for (int ks = 0; ks < ksteps; ++ks) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + stage * WGP_STAGE_BYTES);
+        const uint64_t adesc = make_smem_desc(sa, WGP_CHUNK, SBO, LAYOUT_SW128);
+        const uint64_t bdesc = make_smem_desc(sa + WGP_A_BYTES, WGP_CHUNK, SBO, LAYOUT_SW128);
+#pragma unroll
+        for (int k = 0; k < WG_KP / 16; ++k)
+          umma_bf16_pair(tmem_base, adesc + (uint64_t)(k * KADV), bdesc + (uint64_t)(k * KADV), idesc, (ks > 0 || k > 0) ? 1u : 0u);
+        umma_commit_pair(&empty_bar[stage], 3);
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+      umma_commit_pair(tmem_full, 3);
+    }
+  } else {
+    const int q = warp & 3;
+    const int row = q * 32 + lane;            // output channel within this CTA's 128-tile
+    float* out = P.partial + ((((long long)split * P.taps + tap) * (P.co_tiles * BM) + cot * BM + row) * (long long)P.ci) + cit * 256;
+    if (ksteps > 0) {
+      mbar_wait(tmem_full, 0);
+      tc_fence_after();
+    }
+#pragma unroll 1
+    for (int cc = 0; cc < 256; cc += 32) {
+      float v[32];
+      if (ksteps > 0) {
+        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)cc, v);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = 0.f;
+      }
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(out + cc + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc_pair(tmem_base, 256);
+  }
+}
+
 // dw[co][ci][tap] = sum_split partial[split][tap][co][ci]   (co < co_real, ci < ci_real)
 // partial is [split][tap][m_pad][n_pad]; (m,n) = (co,ci), or (ci,co) when the operand roles were swapped
 __global__ void wgrad_finalize_kernel(const float* __restrict__ partial, float* __restrict__ dw, int splits, int taps,
@@ -703,6 +1032,7 @@ struct WgradPlan {
   int stages, occupancy;
   uint32_t a_bytes, stage_bytes, bar_offset, smem_bytes;
   int swapped;      // 1: M operand = X (input channels), N operand = dY — for heads with few output channels
+  int pair;         // 1: CTA-pair kernel (cta_group::2, M = 256 output channels per pair)
   int64_t ws_bytes;
 };
 
@@ -737,6 +1067,25 @@ static bool plan_wgrad(const nemar_tensor* x, const nemar_tensor* dy, int kh, in
   const uint32_t chunk_a = WG_KP * p.CA * 2, b_bytes = (uint32_t)(p.BN / p.CB) * WG_KP * p.CB * 2;
   p.a_bytes = a_chunks * chunk_a;
   p.stage_bytes = p.a_bytes + b_bytes;
+  p.pair = (pair_mode() > 0 && !p.swapped && p.CA == 64 && p.CB == 64 && p.BN == 256 && mop->c % 256 == 0) ? 1 : 0;
+  if (p.pair) {
+    static const int st_env = [] { const char* e = getenv("NEMAR_WG_PAIR_STAGES"); return e ? atoi(e) : 6; }();
+    p.stages = st_env < 2 ? 2 : (st_env > WGP_MAX_STAGES ? WGP_MAX_STAGES : st_env);
+    p.a_bytes = WGP_A_BYTES;
+    p.stage_bytes = WGP_STAGE_BYTES;
+    p.bar_offset = (uint32_t)p.stages * WGP_STAGE_BYTES;
+    p.smem_bytes = (uint32_t)wgrad_pair_smem_bytes(p.stages);
+    int occ = (int)(233472 / (p.smem_bytes + 1024));
+    p.occupancy = occ < 1 ? 1 : (occ > 2 ? 2 : occ);        // 256 TMEM columns per CTA
+    int splits = (sm_count() * p.occupancy) / base;
+    if (splits > total / 8) splits = total / 8;
+    if (splits > total) splits = total;
+    if (splits < 1) splits = 1;
+    p.tiles_per_split = (total + splits - 1) / splits;
+    p.splits = (total + p.tiles_per_split - 1) / p.tiles_per_split;
+    p.ws_bytes = (int64_t)p.splits * p.taps * p.co_tiles * BM * nop->c * 4;
+    return true;
+  }
   const uint32_t slack = (na_full - a_chunks) * chunk_a;
   // residency: as many CTAs per SM (<= 4, TMEM permitting) as still leaves each a ring of >= 4 stages
   const int tmem_cols = p.BN <= 32 ? 32 : (p.BN <= 64 ? 64 : (p.BN <= 128 ? 128 : 256));
@@ -778,6 +1127,29 @@ static int launch_wgrad_t(const CUtensorMap& tmDY, const CUtensorMap& tmX, const
   }
   dim3 grid((unsigned)(pl.taps * pl.co_tiles * pl.ci_tiles), (unsigned)pl.splits);
   tc_wgrad_kernel<CA, CB, BN><<<grid, NTHREADS, pl.smem_bytes, s>>>(tmDY, tmX, P);
+  NEMAR_LAUNCH_CHECK();
+  return 0;
+}
+
+static int launch_wgrad_pair(const CUtensorMap& tmDY, const CUtensorMap& tmX, const WgradParams& P, const WgradPlan& pl, cudaStream_t s) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(tc_wgrad_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)wgrad_pair_smem_bytes(WGP_MAX_STAGES));
+    NEMAR_REQUIRE(e == cudaSuccess, "cudaFuncSetAttribute(wgrad pair) failed: %s", cudaGetErrorString(e));
+    attr_set = true;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(pl.taps * pl.co_tiles * pl.ci_tiles), (unsigned)pl.splits, 1);   // co_tiles is even: 2 CTAs per pair
+  cfg.blockDim = dim3(NTHREADS, 1, 1);
+  cfg.dynamicSmemBytes = pl.smem_bytes;
+  cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, tc_wgrad_pair_kernel, tmDY, tmX, P);
+  NEMAR_REQUIRE(e == cudaSuccess, "tc_wgrad_pair_kernel launch failed: %s", cudaGetErrorString(e));
   NEMAR_LAUNCH_CHECK();
   return 0;
 }
@@ -843,7 +1215,8 @@ int tc_wgrad(const nemar_tensor* x_in, const nemar_tensor* dy, float* dw, int co
   P.shift_on_a = pl.swapped;
   P.partial = (float*)workspace;
   P.stages = pl.stages; P.a_bytes = pl.a_bytes; P.stage_bytes = pl.stage_bytes; P.bar_offset = pl.bar_offset;
-  if (pl.CA == 64) rc = launch_wgrad_a<64>(tmDY, tmX, P, pl, s);
+  if (pl.pair) rc = launch_wgrad_pair(tmDY, tmX, P, pl, s);
+  else if (pl.CA == 64) rc = launch_wgrad_a<64>(tmDY, tmX, P, pl, s);
   else if (pl.CA == 32) rc = launch_wgrad_a<32>(tmDY, tmX, P, pl, s);
   else rc = launch_wgrad_a<16>(tmDY, tmX, P, pl, s);
   if (rc) return rc;

@@ -34,7 +34,14 @@ CASES = [
     (32, 2, 3, 1, 1, False, 0, 2, 32, 32, 0, True, "offset head 32->2, fp32 out"),
     (512, 1, 4, 1, 1, False, 0, 2, 9, 9, 0, True, "PatchGAN prediction 512->1, fp32 out"),
     (256, 256, 3, 1, 1, False, 0, 2, 4, 4, 0, False, "affine STN 256->256 on 4x4"),
+    # ---- CTA-pair (cta_group::2) geometries: odd tile counts, several 256-channel tiles on either side
+    (256, 256, 3, 1, 1, False, 1, 3, 8, 16, 0, False, "256->256 reflect, 3 destination tiles (pair tail)"),
+    (256, 512, 3, 1, 1, False, 0, 2, 16, 16, L.ACT_LRELU, False, "256->512: two 256-channel destination tiles, two wgrad pairs"),
+    (512, 256, 3, 1, 1, False, 0, 2, 16, 16, 0, False, "512->256: 8 k-chunks per tap, two 256-channel wgrad N tiles"),
 ]
+
+# cases with a 256-multiple channel count on a tensor-core destination (fprop: cout, dgrad: cin) or in the wgrad
+PAIR_CASES = [i for i, c in enumerate(CASES) if (c[0] % 256 == 0 or c[1] % 256 == 0) and not c[11]]
 
 
 def _mk(case, seed=0):

@@ -11,3 +11,28 @@ def test_tc_engine_matches_generic(idx):
     res = tc_cases.run_case(idx, vs_cpu=(idx % 3 == 0))
     bad = tc_cases.check(res)
     assert not bad, "%s: out of tolerance %s in %s" % (res["case"], bad, res)
+
+
+def _pair_is_default():
+    from nemar_b200.engine import lib as L
+    import ctypes as C
+    return L.lib().nemar_conv2d_set_option(C.c_char_p(b"pair"), C.c_int(-1)) > 0
+
+
+def test_tc_pair_mode_matches_generic():
+    """CTA-pair kernels (tcgen05 cta_group::2) on every geometry they take.  Runs in a child process with
+    NEMAR_TC_PAIR=1 (a device trap must not poison this process's context); until the pair mode is the engine's
+    default the test runs only when NEMAR_TEST_PAIR=1."""
+    import json, os, subprocess, sys
+    if not (os.environ.get("NEMAR_TEST_PAIR") or _pair_is_default()):
+        pytest.skip("pair mode is opt-in (NEMAR_TC_PAIR=1); set NEMAR_TEST_PAIR=1 to test it")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = ("import sys, json; sys.path.insert(0, %r); from tests import tc_cases as t\n"
+            "for i in t.PAIR_CASES:\n"
+            "    r = t.run_case(i, True); r['bad'] = t.check(r); print('RES ' + json.dumps(r), flush=True)\n") % root
+    env = dict(os.environ, NEMAR_TC_PAIR="1")
+    p = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600, env=env)
+    res = [json.loads(l[4:]) for l in p.stdout.splitlines() if l.startswith("RES ")]
+    assert p.returncode == 0 and len(res) == len(tc_cases.PAIR_CASES), (p.returncode, p.stderr[-1500:])
+    bad = [r for r in res if r["bad"]]
+    assert not bad, bad
