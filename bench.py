@@ -108,6 +108,8 @@ def run_engine(args):
     if args.cuda_graph:
         extra += ["--cuda_graph", "1"]
         args.kernel_timing = 0
+    if args.batch_d >= 0:
+        extra += ["--batch_d", str(args.batch_d)]
     model, opt = build_engine_model(args.batch, args.size, args.precision, args.conv_engine, extra=extra)
     # the global batch is drawn once (seed 1) and sliced by rank so that 1-GPU and N-GPU runs see the same data
     g = torch.Generator().manual_seed(1)
@@ -196,7 +198,7 @@ def run_engine(args):
                           args.size, args.size, args.batch, args.multi_resolution, args.lambda_smooth, args.alpha),
                       "global_batch": global_batch, "parallelism": "dp%d" % world, "conv_engine": args.conv_engine,
                       "l2": "inputs larger than L2: a step streams several GB of activations, no flush needed",
-                      "cuda_graph": bool(args.cuda_graph),
+                      "cuda_graph": bool(args.cuda_graph), "batch_d": int(getattr(opt, "batch_d", 0)),
                       "allreduce_per_step": 2},
            "clocks": clocks,
            "e2e": {"value": round(e2e_value, 3), "unit": "samples/s", "h2d_bytes_per_step": int(A_host.numel() * 4 * 2),
@@ -348,6 +350,7 @@ def main():
     ap.add_argument("--lambda_smooth", type=float, default=0.0, help="STN regulariser weight (C4: 200)")
     ap.add_argument("--alpha", type=float, default=0.0, help="bilateral alpha of the smoothness term (C4: 1.0)")
     ap.add_argument("--multires_reg", type=int, default=1)
+    ap.add_argument("--batch_d", type=int, default=-1, help="-1: the engine's default; 0/1: one discriminator pass per (A, B) pair / per phase")
     ap.add_argument("--cuda_graph", type=int, default=0, help="capture the step in a CUDA graph (kernel timing is then off)")
     ap.add_argument("--top", type=int, default=4, help="shapes listed per kernel class in roofline.by_kernel")
     ap.add_argument("--kernel_timing", type=int, default=1, help="time conv launches with CUDA events (roofline)")

@@ -80,6 +80,51 @@ class ImagesToNHWC(Function):
         return (None, None, None, None, *grads)
 
 
+class ImageGroupsToNHWC(Function):
+    """Batch-concatenation of several channel-concatenations: group j = cat(imgs[j*m : (j+1)*m], dim=1) fills the
+    samples [j*n, (j+1)*n) of ONE engine tensor, so that a network can take several (A, B_j) pairs in one pass
+    (InstanceNorm keeps samples independent, so this equals separate passes).  The same image may appear in
+    several groups (autograd sums its gradients)."""
+
+    @staticmethod
+    def forward(ctx, pad, pad_mode, dtype, cp, groups, *imgs):
+        imgs = [_c(i) for i in imgs]
+        m = len(imgs) // groups
+        assert m * groups == len(imgs)
+        n, _, h, w = imgs[0].shape
+        chans = [int(i.shape[1]) for i in imgs[:m]]
+        ctot = sum(chans)
+        cp = max(cp, ctot)
+        out = torch.empty((groups * n, h + 2 * pad, w + 2 * pad, cp), dtype=dtype, device=imgs[0].device)
+        if cp > ctot:
+            call("nemar_fill_channels", view(out, pad), ctot, cp - ctot, stream())
+        for j in range(groups):
+            part, coff = out[j * n:(j + 1) * n], 0
+            for img, c in zip(imgs[j * m:(j + 1) * m], chans):
+                assert img.dtype == torch.float32 and tuple(img.shape) == (n, c, h, w)
+                call("nemar_nchw_to_nhwc", fptr(img), view(part, pad, coff, c), pad_mode, stream())
+                coff += c
+        ctx.meta = (pad, pad_mode, chans, (n, h, w), groups)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        pad, pad_mode, chans, (n, h, w), groups = ctx.meta
+        g = _c(g)
+        grads = []
+        for j in range(groups):
+            part, coff = g[j * n:(j + 1) * n], 0
+            for k, c in enumerate(chans):
+                if ctx.needs_input_grad[5 + j * len(chans) + k]:
+                    d = torch.empty((n, c, h, w), dtype=torch.float32, device=g.device)
+                    call("nemar_nhwc_to_nchw", view(part, pad, coff, c), fptr(d), pad_mode, 0, stream())
+                    grads.append(d)
+                else:
+                    grads.append(None)
+                coff += c
+        return (None, None, None, None, None, *grads)
+
+
 class ToNCHW(Function):
     """engine tensor (first c channels) -> NCHW fp32 image."""
 
@@ -653,6 +698,37 @@ class MSEConstFn(Function):
         if pred.shape[3] > c:
             call("nemar_fill_channels", view(dp), c, pred.shape[3] - c, stream())
         call("nemar_mse_const_bwd", view(pred, 0, 0, c), float(target), float(scale), fptr(g), view(dp, 0, 0, c), stream())
+        return dp, None, None, None
+
+
+class MSEConstGroupsFn(Function):
+    """LSGAN terms of a batch-concatenated prediction: out[j] = scale * mean((pred[j*n:(j+1)*n] - targets[j])^2)."""
+
+    @staticmethod
+    def forward(ctx, pred, targets, scale, c=None):
+        pred = _c(pred)
+        k = len(targets)
+        n = pred.shape[0] // k
+        assert n * k == pred.shape[0]
+        c = pred.shape[3] if c is None else c
+        out = torch.zeros(k, dtype=torch.float32, device=pred.device)
+        for j, t in enumerate(targets):
+            call("nemar_mse_const_fwd", view(pred[j * n:(j + 1) * n], 0, 0, c), float(t), float(scale), fptr(out[j:j + 1]), stream())
+        ctx.save_for_backward(pred)
+        ctx.meta = (tuple(targets), scale, c, n)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        (pred,) = ctx.saved_tensors
+        targets, scale, c, n = ctx.meta
+        g = _c(g.reshape(len(targets)).to(torch.float32))
+        dp = torch.empty_like(pred)
+        if pred.shape[3] > c:
+            call("nemar_fill_channels", view(dp), c, pred.shape[3] - c, stream())
+        for j, t in enumerate(targets):
+            call("nemar_mse_const_bwd", view(pred[j * n:(j + 1) * n], 0, 0, c), float(t), float(scale), fptr(g[j:j + 1]),
+                 view(dp[j * n:(j + 1) * n], 0, 0, c), stream())
         return dp, None, None, None
 
 

@@ -33,6 +33,10 @@ class NEMARModel(BaseModel):
                             help="[engine, EXPERIMENTAL] 1: capture optimize_parameters in a CUDA graph after 3 eager steps "
                                  "and replay it.  Capture currently aborts with cudaErrorStreamCaptureIsolation inside "
                                  "autograd's end-of-backward stream sync (DESIGN.md section 7); leave at 0")
+        parser.add_argument("--batch_d", type=int, default=0,
+                            help="[engine] 1: the discriminator evaluates its (A, B_k) pairs of one phase (real / fake_TR / "
+                                 "fake_RT) in ONE pass over their batch-concatenation instead of one pass each "
+                                 "(InstanceNorm keeps samples independent: same losses and gradients, a third of the launches)")
         if is_train:
             parser.add_argument("--lambda_GAN", type=float, default=1.0, help="weight of the GAN loss")
             parser.add_argument("--lambda_recon", type=float, default=100.0, help="weight of the L1 reconstruction loss")
@@ -134,13 +138,33 @@ class NEMARModel(BaseModel):
             total = term if total is None else total + term
         return total
 
+    def _gan_groups(self, pyr_A, imgs_B, targets_are_real, detach):
+        """[sum over scales of GANLoss(D_i(cat(A_i, B_i)), target)  for B, target in zip(imgs_B, targets)], with ONE
+        discriminator pass per scale over the batch-concatenation of all the (A, B) pairs"""
+        total = None
+        for i, netD in enumerate(self._scales()):
+            imgs = []
+            for b in imgs_B:
+                imgs += [pyr_A[i], self._resized(b.detach() if detach else b, i)]
+            pred = netD.forward_engine(*imgs, groups=len(imgs_B))
+            terms = self.criterionGAN.engine_groups(pred, targets_are_real)
+            total = terms if total is None else total + terms
+        return [total[j] for j in range(len(imgs_B))]
+
+    def _batch_d(self):
+        return bool(getattr(self.opt, "batch_d", 0)) and self.opt.gan_mode == "lsgan"
+
     def backward_T_and_R(self):
         opt = self.opt
         pyr_A = self._real_A_pyramid()
         self.loss_L1_TR = F.L1Fn.apply(self.fake_TR_B, self.real_B, opt.lambda_recon).squeeze(0)
-        self.loss_GAN_TR = opt.lambda_GAN * self._gan(pyr_A, self.fake_TR_B, True, detach=False)
         self.loss_L1_RT = F.L1Fn.apply(self.fake_RT_B, self.real_B, opt.lambda_recon).squeeze(0)
-        self.loss_GAN_RT = opt.lambda_GAN * self._gan(pyr_A, self.fake_RT_B, True, detach=False)
+        if self._batch_d():
+            g_tr, g_rt = self._gan_groups(pyr_A, [self.fake_TR_B, self.fake_RT_B], [True, True], detach=False)
+            self.loss_GAN_TR, self.loss_GAN_RT = opt.lambda_GAN * g_tr, opt.lambda_GAN * g_rt
+        else:
+            self.loss_GAN_TR = opt.lambda_GAN * self._gan(pyr_A, self.fake_TR_B, True, detach=False)
+            self.loss_GAN_RT = opt.lambda_GAN * self._gan(pyr_A, self.fake_RT_B, True, detach=False)
         self.loss_smoothness = opt.lambda_smooth * self.stn_reg_term
         loss = self.loss_L1_TR + self.loss_L1_RT + self.loss_GAN_TR + self.loss_GAN_RT + self.loss_smoothness
         loss.backward()
@@ -148,9 +172,13 @@ class NEMARModel(BaseModel):
 
     def backward_D(self):
         pyr_A = self._real_A_pyramid()
-        loss_D_real = self._gan(pyr_A, self.real_B, True, detach=True)
-        self.loss_D_fake_TR = self._gan(pyr_A, self.fake_TR_B, False, detach=True)
-        self.loss_D_fake_RT = self._gan(pyr_A, self.fake_RT_B, False, detach=True)
+        if self._batch_d():
+            loss_D_real, self.loss_D_fake_TR, self.loss_D_fake_RT = self._gan_groups(
+                pyr_A, [self.real_B, self.fake_TR_B, self.fake_RT_B], [True, False, False], detach=True)
+        else:
+            loss_D_real = self._gan(pyr_A, self.real_B, True, detach=True)
+            self.loss_D_fake_TR = self._gan(pyr_A, self.fake_TR_B, False, detach=True)
+            self.loss_D_fake_RT = self._gan(pyr_A, self.fake_RT_B, False, detach=True)
         self.loss_D = 0.5 * self.opt.lambda_GAN * (loss_D_real + self.loss_D_fake_TR + self.loss_D_fake_RT)
         self.loss_D.backward()
         return self.loss_D
@@ -186,7 +214,11 @@ class NEMARModel(BaseModel):
         try:
             torch.cuda.synchronize()
             graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph, capture_error_mode=os.environ.get("NEMAR_GRAPH_CAPTURE_MODE", "thread_local")):
+            # capture on the SAME side stream the warm-up ran on: every autograd node (and every parameter's gradient
+            # accumulator) is then bound to the capturing stream, so the backward pass needs no cross-stream event
+            # (an event recorded outside the capture and waited on inside it is cudaErrorStreamCaptureIsolation)
+            with torch.cuda.graph(graph, stream=st.get("side"),
+                                  capture_error_mode=os.environ.get("NEMAR_GRAPH_CAPTURE_MODE", "thread_local")):
                 self._optimize_parameters_eager()
             st["graph"] = graph
             graph.replay()                    # the capture itself does not execute the step

@@ -209,9 +209,14 @@ class NLayerDiscriminator(nn.Module):
         self.last = idx
         self.model = m
 
-    def forward_engine(self, *imgs):
+    def forward_engine(self, *imgs, groups=1):
+        """imgs: the images whose channel-concatenation is the input; with groups > 1, `groups` consecutive such
+        tuples, evaluated as ONE pass over their batch-concatenation (prediction samples are group-major)."""
         m = self.model
-        t = F.ImagesToNHWC.apply(0, L.PAD_ZERO, CONFIG.dtype, image_channels(self.input_nc), *imgs)
+        if groups > 1:
+            t = F.ImageGroupsToNHWC.apply(0, L.PAD_ZERO, CONFIG.dtype, image_channels(self.input_nc), groups, *imgs)
+        else:
+            t = F.ImagesToNHWC.apply(0, L.PAD_ZERO, CONFIG.dtype, image_channels(self.input_nc), *imgs)
         t = getattr(m, "0").run(t, act=L.ACT_LRELU)
         for idx in self.mid:
             t = conv_in_act(getattr(m, str(idx)), t, 0, L.ACT_LRELU)
@@ -244,6 +249,12 @@ class GANLoss(nn.Module):
         if self.gan_mode == "lsgan":
             return F.MSEConstFn.apply(prediction, target, 1.0, 1).squeeze(0)
         return self.__call__(F.ToNCHW.apply(prediction, 1), target_is_real)
+
+    def engine_groups(self, prediction, targets_are_real):
+        """LSGAN terms of a group-major batch-concatenated prediction -> tensor [len(targets_are_real)]."""
+        assert self.gan_mode == "lsgan"
+        targets = [self.real_value if t else self.fake_value for t in targets_are_real]
+        return F.MSEConstGroupsFn.apply(prediction, targets, 1.0, 1)
 
     def __call__(self, prediction, target_is_real):
         target = self.real_value if target_is_real else self.fake_value

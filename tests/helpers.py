@@ -23,12 +23,12 @@ def engine_opt(cfg, batch, extra, precision="fp32", conv_engine="generic", gpu_i
     return TrainOptions().parse(argv, quiet=True)
 
 
-def build_case(name, precision="fp32", conv_engine="generic", seed=11, gpu_ids="0"):
+def build_case(name, precision="fp32", conv_engine="generic", seed=11, gpu_ids="0", more_flags=()):
     """-> (engine model with the seeded weights loaded, oracle cfg, (T,R,Ds) states, (A,B) batch)"""
     from nemar_b200.models import create_model
     kw, batch, extra = CASE_FLAGS[name]
     cfg = O.OracleConfig(**kw)
-    opt = engine_opt(cfg, batch, extra, precision, conv_engine, gpu_ids)
+    opt = engine_opt(cfg, batch, list(extra) + list(more_flags), precision, conv_engine, gpu_ids)
     model = create_model(opt)
     T, R, Ds = O.make_states(cfg, seed=seed)
     load_states(model, T, R, Ds)
