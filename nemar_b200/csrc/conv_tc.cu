@@ -599,12 +599,15 @@ static int launch_gather_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, co
   return 0;
 }
 
-// 0: single-CTA tiles everywhere; 1: CTA pairs (cta_group::2, 256x256 tiles) for destinations of k*256 channels
+// 0: single-CTA tiles everywhere; 1: CTA pairs (cta_group::2, 256x256 tiles) wherever a side has k*256 channels;
+// 2: pairs in the gather kernel only; 3: pairs in the weight-gradient kernel only
 static int g_pair_mode = -1;
 static int pair_mode() {
   if (g_pair_mode < 0) { const char* e = getenv("NEMAR_TC_PAIR"); g_pair_mode = e ? atoi(e) : 0; }
   return g_pair_mode;
 }
+static bool pair_gather() { const int m = pair_mode(); return m == 1 || m == 2; }
+static bool pair_wgrad() { const int m = pair_mode(); return m == 1 || m == 3; }
 
 static bool tc_view_ok(const nemar_tensor* t, bool allow_f32) {
   const bool dt_ok = t->dtype == NEMAR_BF16 || (allow_f32 && t->dtype == NEMAR_F32);
@@ -622,7 +625,7 @@ static int gather_bn(int cd, int bk, bool f32) {
 bool tc_engine_built() { return true; }
 
 int tc_set_option(const char* key, int value) {
-  if (key && !strcmp(key, "pair")) { const int old = pair_mode(); if (value >= 0) g_pair_mode = value ? 1 : 0; return old; }
+  if (key && !strcmp(key, "pair")) { const int old = pair_mode(); if (value >= 0) g_pair_mode = value > 3 ? 1 : value; return old; }
   return -1;
 }
 
@@ -645,7 +648,7 @@ int tc_gather_gemm(const nemar_tensor* src_in, const nemar_tensor* dst_in, const
   dst.h += 2 * dst.pad; dst.w += 2 * dst.pad; dst.pad = 0;
   const int BK = chunk_for(src.c);
   const bool f32 = dst.dtype == NEMAR_F32;
-  const bool pair = pair_mode() > 0 && dst.c % PAIR_BN == 0 && BK == PAIR_BK && !f32;
+  const bool pair = pair_gather() && dst.c % PAIR_BN == 0 && BK == PAIR_BK && !f32;
   const int BN = pair ? PAIR_BN / 2 : gather_bn(dst.c, BK, f32);     // pair: TMA box = one CTA's half of the weight rows
   const int esz = f32 ? 4 : 2;
   const int taps_total = gg.kh * gg.kw;
@@ -1067,7 +1070,7 @@ static bool plan_wgrad(const nemar_tensor* x, const nemar_tensor* dy, int kh, in
   const uint32_t chunk_a = WG_KP * p.CA * 2, b_bytes = (uint32_t)(p.BN / p.CB) * WG_KP * p.CB * 2;
   p.a_bytes = a_chunks * chunk_a;
   p.stage_bytes = p.a_bytes + b_bytes;
-  p.pair = (pair_mode() > 0 && !p.swapped && p.CA == 64 && p.CB == 64 && p.BN == 256 && mop->c % 256 == 0) ? 1 : 0;
+  p.pair = (pair_wgrad() && !p.swapped && p.CA == 64 && p.CB == 64 && p.BN == 256 && mop->c % 256 == 0) ? 1 : 0;
   if (p.pair) {
     static const int st_env = [] { const char* e = getenv("NEMAR_WG_PAIR_STAGES"); return e ? atoi(e) : 6; }();
     p.stages = st_env < 2 ? 2 : (st_env > WGP_MAX_STAGES ? WGP_MAX_STAGES : st_env);
