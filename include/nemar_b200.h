@@ -58,7 +58,7 @@ int nemar_conv2d_tc_supported(const nemar_conv_geom* g, int dtype, int h_in, int
 /* Engine tuning switch (process-wide; not a semantic option — results stay within the same tolerance).
  *   "pair": 1 = destinations of k*256 channels run on CTA pairs (tcgen05 cta_group::2, 256x256 tiles), 0 = single-CTA
  *   tiles, 2 / 3 = pairs only in the fprop+dgrad / only in the wgrad kernel.  value < 0 only queries.  Returns the previous value, or -1 for an unknown key.  Initial value:
- *   environment NEMAR_TC_PAIR. */
+ *   environment NEMAR_TC_PAIR, else 3. */
 int nemar_conv2d_set_option(const char* key, int value);
 
 /* ---------------------------------------------------------------------------------------------

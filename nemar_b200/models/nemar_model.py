@@ -16,6 +16,7 @@ from . import networks
 from . import stn
 from .base_model import BaseModel
 from ..engine import functional as F
+from ..engine import lib as L
 from ..engine import parallel
 from ..engine.config import configure
 from ..engine.optim import FlatAdam
@@ -30,9 +31,9 @@ class NEMARModel(BaseModel):
         parser.add_argument("--conv_engine", type=str, default="auto", choices=["auto", "generic"],
                             help="[engine] auto: tcgen05 where supported; generic: CUDA-core kernels only")
         parser.add_argument("--cuda_graph", type=int, default=0,
-                            help="[engine, EXPERIMENTAL] 1: capture optimize_parameters in a CUDA graph after 3 eager steps "
-                                 "and replay it.  Capture currently aborts with cudaErrorStreamCaptureIsolation inside "
-                                 "autograd's end-of-backward stream sync (DESIGN.md section 7); leave at 0")
+                            help="[engine] 1: capture optimize_parameters (forward, both backward passes, the gradient "
+                                 "all-reduces and both Adam launches) in ONE CUDA graph after 3 eager steps and replay it; "
+                                 "inputs are copied into static buffers by set_input")
         parser.add_argument("--batch_d", type=int, default=0,
                             help="[engine] 1: the discriminator evaluates its (A, B_k) pairs of one phase (real / fake_TR / "
                                  "fake_RT) in ONE pass over their batch-concatenation instead of one pass each "
@@ -197,6 +198,7 @@ class NEMARModel(BaseModel):
             return self._optimize_parameters_eager()
         if st["graph"] is not None:
             st["graph"].replay()
+            L.COUNTERS["launches"] += st["launches"]     # the engine calls one replay stands for
             return
         if st["eager_steps"] < 3:            # warm-up: lazy initialisation, allocator pools, packed-weight caches
             st["eager_steps"] += 1
@@ -214,6 +216,7 @@ class NEMARModel(BaseModel):
         try:
             torch.cuda.synchronize()
             graph = torch.cuda.CUDAGraph()
+            n0 = L.COUNTERS["launches"]
             # capture on the SAME side stream the warm-up ran on: every autograd node (and every parameter's gradient
             # accumulator) is then bound to the capturing stream, so the backward pass needs no cross-stream event
             # (an event recorded outside the capture and waited on inside it is cudaErrorStreamCaptureIsolation)
@@ -221,6 +224,7 @@ class NEMARModel(BaseModel):
                                   capture_error_mode=os.environ.get("NEMAR_GRAPH_CAPTURE_MODE", "thread_local")):
                 self._optimize_parameters_eager()
             st["graph"] = graph
+            st["launches"] = L.COUNTERS["launches"] - n0
             graph.replay()                    # the capture itself does not execute the step
         except Exception as e:               # noqa: BLE001 - any capture problem => eager launches
             print("CUDA graph capture failed (%s); continuing with eager launches" % str(e).splitlines()[0])

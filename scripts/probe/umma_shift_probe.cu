@@ -23,14 +23,17 @@ using namespace tc;
 
 struct Cfg { int shift_rows, sbo_bytes, base_offset; };
 
-constexpr int ROWS = 256, KC = 64, NB = 64;
+constexpr int ROWS = 256, NB = 64;
 
+template <int KC>
 __global__ void __launch_bounds__(128) probe_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                                                     const Cfg* cfgs, int ncfg, float* out) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  uint8_t* sA = smem;                       // 256 rows x 128 B
-  uint8_t* sB = smem + ROWS * 128;          // 64 rows x 128 B
+  constexpr uint32_t RB = KC * 2;           // bytes per row: 128 / 64 / 32 -> SWIZZLE_128B / 64B / 32B
+  constexpr uint64_t LAYOUT = KC == 64 ? LAYOUT_SW128 : (KC == 32 ? LAYOUT_SW64 : LAYOUT_SW32);
+  uint8_t* sA = smem;                       // 256 rows
+  uint8_t* sB = smem + ROWS * 128;          // 64 rows
   uint64_t* bars = (uint64_t*)(sB + NB * 128);
   uint32_t* tmem_slot = (uint32_t*)(bars + 2);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -45,7 +48,7 @@ __global__ void __launch_bounds__(128) probe_kernel(const __grid_constant__ CUte
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
   if (threadIdx.x == 0) {
-    mbar_expect_tx(&bars[0], ROWS * 128 + NB * 128);
+    mbar_expect_tx(&bars[0], ROWS * RB + NB * RB);
     tma_load_2d(sA, &tmA, &bars[0], 0, 0);
     tma_load_2d(sB, &tmB, &bars[0], 0, 0);
   }
@@ -55,9 +58,9 @@ __global__ void __launch_bounds__(128) probe_kernel(const __grid_constant__ CUte
     if (threadIdx.x == 0) {
       tc_fence_after();
       const Cfg cf = cfgs[c];
-      uint64_t adesc = make_smem_desc(smem_u32(sA) + (uint32_t)cf.shift_rows * 128u, 16, (uint32_t)cf.sbo_bytes, LAYOUT_SW128);
+      uint64_t adesc = make_smem_desc(smem_u32(sA) + (uint32_t)cf.shift_rows * RB, 16, (uint32_t)cf.sbo_bytes, LAYOUT);
       adesc |= (uint64_t)(cf.base_offset & 7) << 49;
-      const uint64_t bdesc = make_smem_desc(smem_u32(sB), 16, 1024, LAYOUT_SW128);
+      const uint64_t bdesc = make_smem_desc(smem_u32(sB), 16, 8 * RB, LAYOUT);
       for (int k = 0; k < KC / 16; ++k) umma_bf16(tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, k > 0 ? 1u : 0u);
       umma_commit(&bars[1]);
     }
@@ -84,14 +87,12 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); return 1; } } while (0)
 
-int main() {
-  void* p = nullptr;
-  cudaDriverEntryPointQueryResult q;
-  CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q));
-  EncodeTiledFn enc = (EncodeTiledFn)p;
+template <int KC>
+static int run(EncodeTiledFn enc) {
+  constexpr int RB = KC * 2;
   std::vector<__nv_bfloat16> hA(ROWS * KC), hB(NB * KC);
   std::vector<float> fA(ROWS * KC), fB(NB * KC);
-  unsigned s = 12345u;
+  unsigned s = 12345u + KC;
   auto rnd = [&](int lo, int hi) { s = s * 1664525u + 1013904223u; return lo + (int)((s >> 16) % (unsigned)(hi - lo + 1)); };
   for (int i = 0; i < ROWS * KC; ++i) { fA[i] = (float)rnd(-3, 3); hA[i] = __float2bfloat16(fA[i]); }
   for (int i = 0; i < NB * KC; ++i) { fB[i] = (float)rnd(-2, 2); hB[i] = __float2bfloat16(fB[i]); }
@@ -100,41 +101,44 @@ int main() {
   CK(cudaMalloc(&dB, hB.size() * 2));
   CK(cudaMemcpy(dA, hA.data(), hA.size() * 2, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(dB, hB.data(), hB.size() * 2, cudaMemcpyHostToDevice));
+  const CUtensorMapSwizzle sw = KC == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (KC == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
   CUtensorMap tmA, tmB;
   {
     cuuint64_t dims[2] = {KC, ROWS}; cuuint64_t str[1] = {KC * 2}; cuuint32_t box[2] = {KC, ROWS}; cuuint32_t es[2] = {1, 1};
-    CUresult r = enc(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, dA, dims, str, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CUresult r = enc(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, dA, dims, str, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                     CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { printf("encode A failed %d\n", (int)r); return 1; }
     cuuint64_t dimsb[2] = {KC, NB}; cuuint32_t boxb[2] = {KC, NB};
-    r = enc(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, dB, dimsb, str, boxb, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    r = enc(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, dB, dimsb, str, boxb, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+            CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { printf("encode B failed %d\n", (int)r); return 1; }
   }
   std::vector<Cfg> cfgs;
-  const int sbos[3] = {1024, 1280, 2048};
+  const int group_rows[3] = {8, 10, 16};      // rows between consecutive 8-row groups (SBO / row bytes)
   for (int si = 0; si < 3; ++si)
-    for (int sh = 0; sh <= 8; ++sh) {
-      cfgs.push_back({sh, sbos[si], 0});
-      if (sh & 7) cfgs.push_back({sh, sbos[si], sh & 7});
+    for (int sh = 0; sh <= 11; ++sh) {
+      if (sh + 15 * group_rows[si] + 7 >= ROWS) continue;
+      cfgs.push_back({sh, group_rows[si] * RB, 0});
+      if (KC == 64 && (sh & 7) && sh < 8) cfgs.push_back({sh, group_rows[si] * RB, sh & 7});
     }
   Cfg* dC; float* dO;
   CK(cudaMalloc(&dC, cfgs.size() * sizeof(Cfg)));
   CK(cudaMemcpy(dC, cfgs.data(), cfgs.size() * sizeof(Cfg), cudaMemcpyHostToDevice));
   CK(cudaMalloc(&dO, cfgs.size() * 128 * NB * sizeof(float)));
   const int smem = ROWS * 128 + NB * 128 + 1024 + 256;
-  CK(cudaFuncSetAttribute(probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  probe_kernel<<<1, 128, smem>>>(tmA, tmB, dC, (int)cfgs.size(), dO);
+  CK(cudaFuncSetAttribute(probe_kernel<KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  probe_kernel<KC><<<1, 128, smem>>>(tmA, tmB, dC, (int)cfgs.size(), dO);
   CK(cudaGetLastError());
   CK(cudaDeviceSynchronize());
   std::vector<float> hO(cfgs.size() * 128 * NB);
   CK(cudaMemcpy(hO.data(), dO, hO.size() * 4, cudaMemcpyDeviceToHost));
-  printf("UMMA K-major SWIZZLE_128B, M=128 N=64 K=64: A window = rows shift + (m/8)*(SBO/128) + m%%8 of a 256-row TMA tile\n");
+  printf("UMMA K-major SWIZZLE_%dB, M=128 N=64 K=%d: A window = rows shift + (m/8)*(SBO/%d) + m%%8 of a 256-row TMA tile\n", RB, KC, RB);
+  int nmatch = 0;
   for (size_t c = 0; c < cfgs.size(); ++c) {
     const Cfg cf = cfgs[c];
     int good_rows = 0, first_bad = -1;
     for (int m = 0; m < 128; ++m) {
-      const int r = cf.shift_rows + (m / 8) * (cf.sbo_bytes / 128) + (m % 8);
+      const int r = cf.shift_rows + (m / 8) * (cf.sbo_bytes / RB) + (m % 8);
       bool ok = true;
       for (int n = 0; n < NB && ok; ++n) {
         float acc = 0.f;
@@ -143,8 +147,22 @@ int main() {
       }
       if (ok) ++good_rows; else if (first_bad < 0) first_bad = m;
     }
-    printf("PROBE shift=%d sbo=%d base_offset=%d : %s (%d/128 rows exact, first bad row %d)\n", cf.shift_rows, cf.sbo_bytes,
+    nmatch += good_rows == 128;
+    printf("PROBE sw=%dB shift=%d sbo=%d base_offset=%d : %s (%d/128 rows exact, first bad row %d)\n", RB, cf.shift_rows, cf.sbo_bytes,
            cf.base_offset, good_rows == 128 ? "MATCH" : "mismatch", good_rows, first_bad);
   }
+  printf("SUMMARY sw=%dB: %d of %d configurations exact\n", RB, nmatch, (int)cfgs.size());
+  cudaFree(dA); cudaFree(dB); cudaFree(dC); cudaFree(dO);
+  return 0;
+}
+
+int main() {
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q));
+  EncodeTiledFn enc = (EncodeTiledFn)p;
+  if (run<64>(enc)) return 1;
+  if (run<32>(enc)) return 1;
+  if (run<16>(enc)) return 1;
   return 0;
 }
