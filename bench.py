@@ -211,7 +211,7 @@ def run_engine(args):
                           args.size, args.size, args.batch, args.multi_resolution, args.lambda_smooth, args.alpha),
                       "global_batch": global_batch, "parallelism": "dp%d" % world, "conv_engine": args.conv_engine,
                       "l2": "inputs larger than L2: a step streams several GB of activations, no flush needed",
-                      "cuda_graph": graphed, "batch_d": int(getattr(opt, "batch_d", 0)),
+                      "cuda_graph": graphed, "batch_d": int(getattr(opt, "batch_d", 1)),
                       "allreduce_per_step": 2},
            "clocks": clocks,
            "e2e": {"value": round(e2e_value, 3), "unit": "samples/s", "h2d_bytes_per_step": int(A_host.numel() * 4 * 2),
@@ -364,7 +364,9 @@ def main():
     ap.add_argument("--alpha", type=float, default=0.0, help="bilateral alpha of the smoothness term (C4: 1.0)")
     ap.add_argument("--multires_reg", type=int, default=1)
     ap.add_argument("--batch_d", type=int, default=-1, help="-1: the engine's default; 0/1: one discriminator pass per (A, B) pair / per phase")
-    ap.add_argument("--cuda_graph", type=int, default=0, help="capture the step in a CUDA graph (kernel timing is then off)")
+    ap.add_argument("--cuda_graph", type=int, default=1,
+                    help="1 (default): the model captures optimize_parameters in a CUDA graph (its --cuda_graph 1 flag) and the "
+                         "timed region replays it; the roofline figures then come from an eager pass of the same steps")
     ap.add_argument("--top", type=int, default=4, help="shapes listed per kernel class in roofline.by_kernel")
     ap.add_argument("--kernel_timing", type=int, default=1, help="time conv launches with CUDA events (roofline)")
     ap.add_argument("--grid_sample_bench", type=int, default=1)

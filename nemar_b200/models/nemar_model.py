@@ -34,8 +34,8 @@ class NEMARModel(BaseModel):
                             help="[engine] 1: capture optimize_parameters (forward, both backward passes, the gradient "
                                  "all-reduces and both Adam launches) in ONE CUDA graph after 3 eager steps and replay it; "
                                  "inputs are copied into static buffers by set_input")
-        parser.add_argument("--batch_d", type=int, default=0,
-                            help="[engine] 1: the discriminator evaluates its (A, B_k) pairs of one phase (real / fake_TR / "
+        parser.add_argument("--batch_d", type=int, default=1,
+                            help="[engine] 1 (default): the discriminator evaluates its (A, B_k) pairs of one phase (real / fake_TR / "
                                  "fake_RT) in ONE pass over their batch-concatenation instead of one pass each "
                                  "(InstanceNorm keeps samples independent: same losses and gradients, a third of the launches)")
         if is_train:
@@ -153,7 +153,7 @@ class NEMARModel(BaseModel):
         return [total[j] for j in range(len(imgs_B))]
 
     def _batch_d(self):
-        return bool(getattr(self.opt, "batch_d", 0)) and self.opt.gan_mode == "lsgan"
+        return bool(getattr(self.opt, "batch_d", 1)) and self.opt.gan_mode == "lsgan"
 
     def backward_T_and_R(self):
         opt = self.opt
