@@ -141,16 +141,23 @@ def run_engine(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms)
 
-    for _ in range(args.warmup if args.profile else max(args.warmup, 3) + (4 if args.cuda_graph else 0)):
+    def step():
         model.set_input(dev_batch)
         model.optimize_parameters()
+
+    graph_wanted = bool(args.cuda_graph) and not args.profile
+    if not graph_wanted:
+        opt.cuda_graph = 0
+    # graph mode: three eager steps on the capture stream, the capture (+ first replay), then replays
+    for _ in range(args.warmup if args.profile else max(args.warmup, 3) + (4 if graph_wanted else 0)):
+        step()
     torch.cuda.synchronize()
 
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     L.COUNTERS["launches"] = 0
-    graphed = bool(args.cuda_graph) and getattr(model, "_graph_state", {}).get("graph") is not None
+    graphed = graph_wanted and getattr(model, "_graph_state", {}).get("graph") is not None
     L.TIMER.enable(0 if graphed else args.kernel_timing)
     ms = timed(dev_batch, args.steps, read_loss=False)
     launches = L.COUNTERS["launches"]
@@ -159,27 +166,34 @@ def run_engine(args):
     clocks = sampler.stop() if rank == 0 else None
     ms_e2e = timed(host_batch, args.steps, read_loss=True)
     roofline_pass = "the timed region itself (CUDA events around every conv launch on the launching stream)"
-    if graphed and args.kernel_timing:
+    if graphed and args.kernel_timing and world == 1:
         # a graph replay has no place for per-kernel events: the roofline figures come from the SAME K steps launched
-        # eagerly right after the timed (replayed) region — same kernels, same shapes, same stream
-        opt.cuda_graph = 0
-        model.set_input(dev_batch)
-        model.optimize_parameters()
-        L.TIMER.enable(args.kernel_timing)
-        timed(dev_batch, args.steps, read_loss=False)
-        kstats = L.TIMER.collect()
-        L.TIMER.enable(False)
-        opt.cuda_graph = 1
-        roofline_pass = "a separate eager pass of the same %d steps right after the timed region (the timed region replays a CUDA graph)" % args.steps
+        # eagerly right after the timed (replayed) region — same kernels, same shapes, same stream.  (Only at N = 1: the
+        # per-kernel figures do not depend on N, and a multi-rank run stays "eager warm-up, capture, replays only".)
+        try:
+            opt.cuda_graph = 0
+            step()
+            L.TIMER.enable(args.kernel_timing)
+            timed(dev_batch, args.steps, read_loss=False)
+            kstats = L.TIMER.collect()
+            roofline_pass = ("a separate eager pass of the same %d steps right after the timed region (the timed region replays "
+                             "a CUDA graph, which has no place for per-kernel events)" % args.steps)
+        except Exception as e:      # noqa: BLE001 - the headline numbers above are already measured; never lose them
+            sys.stderr.write("roofline pass failed: %r\n" % (e,))
+            kstats = {}
+        finally:
+            L.TIMER.enable(False)
+            opt.cuda_graph = 1
 
     global_batch = args.batch * world
     value = global_batch * args.steps / (ms / 1e3)
     e2e_value = global_batch * args.steps / (ms_e2e / 1e3)
     if world > 1:
         dist.barrier()
+        torch.cuda.synchronize()
     if rank != 0:
         if world > 1:
-            dist.destroy_process_group()
+            leave_process_group(graphed)
         return
     # ---- roofline of the dominant kernel (largest share of timed kernel time)
     roof = None
@@ -202,6 +216,10 @@ def run_engine(args):
                                   "tflops": round(v["flops"] / max(v["ms"], 1e-9) / 1e9, 2),
                                   "top": dict(sorted(((a, round(b, 3)) for a, b in v["top"].items()), key=lambda t: -t[1])[:args.top])}
                               for k, v in sorted(kstats.items(), key=lambda kv: -kv[1]["ms"])}}
+    if roof is None and graphed and world > 1:
+        roof = {"bound": "tensor", "achieved": None, "peak": peaks["tf_sustained"], "unit": "TFLOP/s", "frac": None, "traffic": ncu_traffic,
+                "note": "per-kernel figures are timed at N = 1 (eager pass after the replayed region); a multi-rank run replays "
+                        "the captured step only — see conv_roofline_frac_whole_step for the whole-step figure at this N"}
     conv_frac = value * CONV_GFLOP_PER_SAMPLE * 1e9 / (world * peaks["tf_sustained"] * 1e12) if args.size == HW else None
     out = {"metric": "paired 256x256 samples/sec", "value": round(value, 3), "unit": "samples/s", "n_gpus": world,
            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": round(ms / args.steps, 3),
@@ -220,11 +238,31 @@ def run_engine(args):
            "conv_roofline_frac_whole_step": round(conv_frac, 4) if conv_frac is not None else None,
            "roofline": roof}
     if world == 1 and not args.no_cpu_baseline:
-        out["cpu_baseline"] = cpu_baseline(args.size, budget_s=15.0)
+        try:
+            out["cpu_baseline"] = cpu_baseline(args.size, budget_s=15.0)
+        except Exception as e:      # noqa: BLE001
+            out["cpu_baseline"] = {"error": repr(e)}
     if args.grid_sample_bench:
-        out["grid_sample"] = grid_sample_bench(dev, peaks)
+        try:
+            out["grid_sample"] = grid_sample_bench(dev, peaks)
+        except Exception as e:      # noqa: BLE001
+            out["grid_sample"] = {"error": repr(e)}
     print(json.dumps(out))
     sys.stdout.flush()
+    if world > 1 and graphed:
+        leave_process_group(graphed)
+
+
+def leave_process_group(graphed):
+    """End of a multi-rank run.  After a captured step (NCCL all-reduces inside the CUDA graph) destroy_process_group()
+    does not return (measured at 2 ranks: the communicator teardown waits forever while the graph is alive), so a rank
+    that replayed a graph leaves with os._exit once every rank has passed the final barrier; nothing is pending then."""
+    import torch.distributed as dist
+    sys.stdout.flush()
+    sys.stderr.flush()
+    if graphed:
+        os._exit(0)
+    dist.destroy_process_group()
 
 
 def pick_cpu_threads():
