@@ -476,6 +476,192 @@ tc_gather_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   }
 }
 
+// -------------------------------------------------------------------------------------------------
+// gather kernel, resident-patch variant for stride-1 k x k convolutions with few channels (opt-in: NEMAR_TC_RP3=1)
+// -------------------------------------------------------------------------------------------------
+// The 32/64/96-channel full-resolution layers of the STN spend their time in the per-k-step machinery of the
+// kernel above: nine k-steps of two tiny MMAs each, every one behind its own TMA box and barrier round trip, the
+// same pixels fetched nine times.  Here a PERSISTENT CTA keeps the layer's whole weight pack in shared memory,
+// fetches ONE (TH + kh - 1) x (TW + kw - 1) pixel patch per tile and channel chunk, and feeds every tap's MMA from a
+// shifted WINDOW of that patch: with TW = 8 the window of tap (dy, dx) starts (dy*PW + dx) rows into the patch and
+// its 8-row groups are PW rows apart (SBO = PW rows).  The swizzle XOR is a function of the absolute shared-memory
+// address, so such windows are exact for SWIZZLE_128B/64B/32B (scripts/probe/umma_shift_probe.cu).  Accumulators
+// are multi-buffered in TMEM: the epilogue of tile i overlaps the MMAs of tile i+1 and the TMA of tile i+2.
+constexpr int RP_TW = 8, RP_TH = 16, RP_MAX_STAGES = 8, RP_MAX_ACCS = 4;
+
+struct Rp3Params {
+  GatherParams g;
+  int dy_min, dx_min;        // source offset of the patch origin relative to the tile origin
+  int pw, ph;                // patch extent in pixels
+  uint32_t patch_bytes;      // one channel chunk of one patch, rounded to 1 KB
+  uint32_t wtile_bytes;      // one (tap, chunk) weight tile, rounded to 1 KB
+  uint32_t w_tx_bytes;       // bytes the weight loads deliver
+  int stages, naccs;
+  int tiles_total;
+  int taps_total;            // kh * kw (weight tiles are addressed by the original tap index)
+};
+
+template <int BN, int BK, bool F32OUT>
+__global__ void __launch_bounds__(NTHREADS)
+tc_rp3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+              const __grid_constant__ Rp3Params R) {
+  const GatherParams& P = R.g;
+  constexpr uint32_t ROWB = BK * 2;                       // bytes of one pixel's channel chunk
+  constexpr uint32_t ACC_COLS = BN < 32 ? 32 : BN;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const int wtiles = R.taps_total * P.kchunks;            // weight tiles are indexed by the ORIGINAL tap index
+  uint8_t* wsm = smem;
+  const uint32_t stage_bytes = (uint32_t)P.kchunks * R.patch_bytes;
+  uint8_t* psm = smem + (size_t)wtiles * R.wtile_bytes;
+  uint64_t* full_bar = (uint64_t*)(psm + (size_t)R.stages * stage_bytes);
+  uint64_t* empty_bar = full_bar + RP_MAX_STAGES;
+  uint64_t* tmem_full = empty_bar + RP_MAX_STAGES;
+  uint64_t* tmem_empty = tmem_full + RP_MAX_ACCS;
+  uint64_t* w_bar = tmem_empty + RP_MAX_ACCS;
+  uint32_t* tmem_slot = (uint32_t*)(w_bar + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int c0 = blockIdx.y * BN;
+  const int S = R.stages, NA = R.naccs;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmA);
+    prefetch_tmap(&tmB);
+    for (int s = 0; s < S; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int a = 0; a < NA; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 4); }
+    mbar_init(w_bar, 1);
+    fence_mbar_init();
+  }
+  uint32_t tmem_cols = 32;
+  while (tmem_cols < (uint32_t)NA * ACC_COLS) tmem_cols <<= 1;
+  if (warp == 2) tmem_alloc(tmem_slot, tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== TMA producer: the weight pack once, then one patch per tile =====
+      mbar_expect_tx(w_bar, R.w_tx_bytes);
+      for (int t = 0; t < P.ntaps; ++t)
+        for (int kc = 0; kc < P.kchunks; ++kc) {
+          const int wt = P.twi[t] * P.kchunks + kc;
+          tma_load_3d(wsm + (size_t)wt * R.wtile_bytes, &tmB, w_bar, 0, c0, wt);
+        }
+      int i = 0;
+      for (int tile = blockIdx.x; tile < R.tiles_total; tile += gridDim.x, ++i) {
+        const int stage = i % S;
+        const uint32_t phase = (uint32_t)(i / S) & 1u;
+        int t = tile;
+        const int tx = t % P.tiles_x; t /= P.tiles_x;
+        const int ty = t % P.tiles_y;
+        const int x0 = tx * RP_TW, y0 = ty * RP_TH, n0 = t / P.tiles_y;
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        mbar_expect_tx(&full_bar[stage], (uint32_t)P.kchunks * (uint32_t)(R.pw * R.ph) * ROWB);
+        for (int kc = 0; kc < P.kchunks; ++kc)
+          tma_load_4d(psm + (size_t)stage * stage_bytes + (size_t)kc * R.patch_bytes, &tmA, &full_bar[stage], kc * BK,
+                      x0 + R.dx_min, y0 + R.dy_min, n0);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===== MMA issuer =====
+      constexpr uint32_t idesc = make_idesc_bf16(BM, BN, 0, 0);
+      const uint32_t sbo_a = (uint32_t)R.pw * ROWB;       // 8-row groups = consecutive tile rows, PW pixels apart
+      mbar_wait(w_bar, 0);
+      int i = 0;
+      for (int tile = blockIdx.x; tile < R.tiles_total; tile += gridDim.x, ++i) {
+        const int stage = i % S, a = i % NA;
+        const uint32_t sphase = (uint32_t)(i / S) & 1u, aphase = (uint32_t)(i / NA) & 1u;
+        const uint32_t acc = tmem_base + (uint32_t)a * ACC_COLS;
+        mbar_wait(&tmem_empty[a], aphase ^ 1);            // the epilogue has drained this accumulator
+        mbar_wait(&full_bar[stage], sphase);
+        tc_fence_after();
+        uint32_t first = 0;
+        for (int kc = 0; kc < P.kchunks; ++kc) {
+          const uint32_t pa = smem_u32(psm + (size_t)stage * stage_bytes + (size_t)kc * R.patch_bytes);
+          for (int t = 0; t < P.ntaps; ++t) {
+            const uint32_t win = (uint32_t)((P.tdy[t] - R.dy_min) * R.pw + (P.tdx[t] - R.dx_min)) * ROWB;
+            const uint64_t adesc = make_smem_desc(pa + win, 16, sbo_a, layout_for(BK));
+            const uint64_t bdesc = make_smem_desc(smem_u32(wsm + (size_t)(P.twi[t] * P.kchunks + kc) * R.wtile_bytes), 16,
+                                                  8 * ROWB, layout_for(BK));
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k) {
+              umma_bf16(acc, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, first);
+              first = 1u;
+            }
+          }
+        }
+        umma_commit(&empty_bar[stage]);
+        umma_commit(&tmem_full[a]);
+      }
+    }
+  } else {
+    // ===== epilogue: warps 2..5, TMEM lanes 32*(warp%4) .. +31; lane m of the tile = pixel (m % 8, m / 8) =====
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int rx = row % RP_TW, ry = row / RP_TW;
+    int i = 0;
+    for (int tile = blockIdx.x; tile < R.tiles_total; tile += gridDim.x, ++i) {
+      const int a = i % NA;
+      const uint32_t aphase = (uint32_t)(i / NA) & 1u;
+      int t = tile;
+      const int tx = t % P.tiles_x; t /= P.tiles_x;
+      const int ty = t % P.tiles_y;
+      const int px = tx * RP_TW + rx, py = ty * RP_TH + ry, pn = t / P.tiles_y;
+      const bool valid = px < P.dw && py < P.dh && pn < P.dn;
+      const long long off = (long long)pn * P.ds_n + (long long)py * P.ds_y + (long long)px * P.ds_x + c0;
+      const uint32_t acc = tmem_base + (uint32_t)a * ACC_COLS;
+      mbar_wait(&tmem_full[a], aphase);
+      tc_fence_after();
+      float v[ACC_COLS];
+#pragma unroll
+      for (int cc = 0; cc < (int)ACC_COLS; cc += 32) {
+        float w[32];
+        tmem_ld_32x32(acc + ((uint32_t)(q * 32) << 16) + (uint32_t)cc, w);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[cc + j] = w[j];
+      }
+      // the values are in registers: hand the accumulator back before the stores
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[a]);
+      if (valid) {
+#pragma unroll
+        for (int g = 0; g < (int)ACC_COLS / 8; ++g) {
+          if (g * 8 < BN && c0 + g * 8 < P.cd) {
+            float f[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float b = P.bias ? __ldg(P.bias + c0 + g * 8 + j) : 0.f;
+              f[j] = act_fwd(v[g * 8 + j] + b, P.act);
+            }
+            if constexpr (F32OUT) {
+              float* o = (float*)P.dst + off + g * 8;
+              *reinterpret_cast<float4*>(o) = make_float4(f[0], f[1], f[2], f[3]);
+              *reinterpret_cast<float4*>(o + 4) = make_float4(f[4], f[5], f[6], f[7]);
+            } else {
+              uint4 pk;
+              __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&pk);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) h[j] = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+              *reinterpret_cast<uint4*>((__nv_bfloat16*)P.dst + off + g * 8) = pk;
+            }
+          }
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, tmem_cols);
+  }
+}
+
 // Pixel box (tw x th x tn, all powers of two, product `total`) that wastes the fewest accumulator rows on the
 // (dw x dh x dn) index space: e.g. the 66x66 reflect-padded maps of the ResnetBlock dgrad fill only 52 % of 128x1
 // boxes but 94 % of 4x4x8 ones.  Narrow boxes cost a little TMA efficiency, hence the small penalty below 8 pixels.
@@ -611,6 +797,67 @@ static int pair_mode() {
 static bool pair_gather() { const int m = pair_mode(); return m == 1 || m == 2; }
 static bool pair_wgrad() { const int m = pair_mode(); return m == 1 || m == 3; }
 
+// resident-patch launch: persistent CTAs, one per SM (x output-channel tiles)
+template <int BN, int BK, bool F32OUT>
+static int launch_rp3_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const Rp3Params& R, int ctiles, size_t smem_bytes, cudaStream_t s) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(tc_rp3_kernel<BN, BK, F32OUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+    NEMAR_REQUIRE(e == cudaSuccess, "cudaFuncSetAttribute(rp3) failed: %s", cudaGetErrorString(e));
+    attr_set = true;
+  }
+  int gx = sm_count() / ctiles;
+  if (gx < 1) gx = 1;
+  if (gx > R.tiles_total) gx = R.tiles_total;
+  dim3 grid((unsigned)gx, (unsigned)ctiles);
+  tc_rp3_kernel<BN, BK, F32OUT><<<grid, NTHREADS, smem_bytes, s>>>(tmA, tmB, R);
+  NEMAR_LAUNCH_CHECK();
+  return 0;
+}
+template <int BN>
+static int launch_rp3_k(const CUtensorMap& a, const CUtensorMap& b, const Rp3Params& R, int ct, int bk, bool f32, size_t smem, cudaStream_t s) {
+  if (bk == 64) return f32 ? launch_rp3_t<BN, 64, true>(a, b, R, ct, smem, s) : launch_rp3_t<BN, 64, false>(a, b, R, ct, smem, s);
+  if (bk == 32) return f32 ? launch_rp3_t<BN, 32, true>(a, b, R, ct, smem, s) : launch_rp3_t<BN, 32, false>(a, b, R, ct, smem, s);
+  return f32 ? launch_rp3_t<BN, 16, true>(a, b, R, ct, smem, s) : launch_rp3_t<BN, 16, false>(a, b, R, ct, smem, s);
+}
+
+// Plans the resident-patch kernel for one gather problem; false when it does not apply (then the tiled kernel runs).
+static bool plan_rp3(const GatherParams& P, int taps_total, int BN, int BK, Rp3Params& R, size_t& smem_bytes) {
+  if (BN > 64 || P.ntaps < 2) return false;
+  int dy0 = P.tdy[0], dy1 = P.tdy[0], dx0 = P.tdx[0], dx1 = P.tdx[0];
+  for (int t = 1; t < P.ntaps; ++t) {
+    dy0 = P.tdy[t] < dy0 ? P.tdy[t] : dy0; dy1 = P.tdy[t] > dy1 ? P.tdy[t] : dy1;
+    dx0 = P.tdx[t] < dx0 ? P.tdx[t] : dx0; dx1 = P.tdx[t] > dx1 ? P.tdx[t] : dx1;
+  }
+  if (dy1 - dy0 > 6 || dx1 - dx0 > 6) return false;
+  R.g = P;
+  R.dy_min = dy0; R.dx_min = dx0;
+  R.pw = RP_TW + (dx1 - dx0); R.ph = RP_TH + (dy1 - dy0);
+  const uint32_t rowb = (uint32_t)BK * 2;
+  R.patch_bytes = round1k((uint32_t)(R.pw * R.ph) * rowb);
+  R.wtile_bytes = round1k((uint32_t)BN * rowb);
+  R.w_tx_bytes = (uint32_t)(P.ntaps * P.kchunks) * (uint32_t)BN * rowb;
+  R.taps_total = taps_total;
+  const size_t w_total = (size_t)taps_total * P.kchunks * R.wtile_bytes;
+  const size_t stage = (size_t)P.kchunks * R.patch_bytes;
+  const size_t fixed = 1024 /*alignment*/ + 512 /*barriers*/ + w_total;
+  if (fixed + 2 * stage > 232448) return false;
+  static const int st_env = [] { const char* e = getenv("NEMAR_TC_RP3_STAGES"); return e ? atoi(e) : 6; }();
+  int stages = (int)((232448 - fixed) / stage);
+  if (stages > st_env) stages = st_env;
+  if (stages > RP_MAX_STAGES) stages = RP_MAX_STAGES;
+  if (stages < 2) return false;
+  R.stages = stages;
+  R.naccs = RP_MAX_ACCS;
+  R.g.tw = RP_TW; R.g.th = RP_TH; R.g.tn = 1;
+  R.g.tiles_x = (P.dw + RP_TW - 1) / RP_TW;
+  R.g.tiles_y = (P.dh + RP_TH - 1) / RP_TH;
+  R.g.tiles_n = P.dn;
+  R.tiles_total = R.g.tiles_x * R.g.tiles_y * R.g.tiles_n;
+  smem_bytes = fixed + (size_t)stages * stage;
+  return true;
+}
+
 static bool tc_view_ok(const nemar_tensor* t, bool allow_f32) {
   const bool dt_ok = t->dtype == NEMAR_BF16 || (allow_f32 && t->dtype == NEMAR_F32);
   return dt_ok && t->c % 16 == 0 && t->cs % 8 == 0 && t->coff % 8 == 0 && ((((uintptr_t)t->ptr) & 15) == 0);
@@ -706,6 +953,24 @@ int tc_gather_gemm(const nemar_tensor* src_in, const nemar_tensor* dst_in, const
     //  reduction pass costs, so the fused variant is opt-in: NEMAR_FUSED_STATS=1)
     P.stats = (fuse && stats && P.tn == 1 && !f32) ? stats : nullptr;
     if (stats && !P.stats) fused_stats = false;
+    static const int rp3_env = [] { const char* e = getenv("NEMAR_TC_RP3"); return e ? atoi(e) : 0; }();
+    if (rp3_env && !pair && gg.sm == 1 && gg.sd == 1 && !P.stats) {
+      Rp3Params R;
+      size_t rp_smem = 0;
+      if (plan_rp3(P, taps_total, BN, BK, R, rp_smem)) {
+        CUtensorMap tmP;
+        rc = make_act_map(&tmP, &src, BK, R.pw, R.ph, 1, 1);
+        if (rc) return rc;
+        const int ct = (dst.c + BN - 1) / BN;
+        switch (BN) {
+          case 64: rc = launch_rp3_k<64>(tmP, tmB, R, ct, BK, f32, rp_smem, s); break;
+          case 32: rc = launch_rp3_k<32>(tmP, tmB, R, ct, BK, f32, rp_smem, s); break;
+          default: rc = launch_rp3_k<16>(tmP, tmB, R, ct, BK, f32, rp_smem, s); break;
+        }
+        if (rc) return rc;
+        continue;
+      }
+    }
     CUtensorMap tmA;
     rc = make_act_map(&tmA, &src, BK, P.tw, P.th, P.tn, gg.sm);
     if (rc) return rc;

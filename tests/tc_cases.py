@@ -116,3 +116,7 @@ TOL = {"fwd": 6e-3, "stats": 1e-3, "dgrad": 6e-3, "wgrad": 4e-3, "bias": 1e-3, "
 
 def check(res):
     return [k for k, v in res.items() if k in TOL and not (v <= TOL[k])]
+
+# stride-1 k x k geometries the resident-patch kernel (NEMAR_TC_RP3=1) takes: <= 64 output channels per tile, weight pack
+# and two patches within shared memory (fprop and/or dgrad side)
+RP3_CASES = [i for i, c in enumerate(CASES) if c[2] > 1 and c[3] == 1 and not c[5] and (c[0] <= 96 or c[1] <= 96)]

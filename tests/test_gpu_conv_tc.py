@@ -36,3 +36,22 @@ def test_tc_pair_mode_matches_generic():
     assert p.returncode == 0 and len(res) == len(tc_cases.PAIR_CASES), (p.returncode, p.stderr[-1500:])
     bad = [r for r in res if r["bad"]]
     assert not bad, bad
+
+
+def test_tc_resident_patch_mode_matches_generic():
+    """Resident-patch kernel (tap-shifted UMMA windows over one TMA patch; opt-in NEMAR_TC_RP3=1) on every stride-1
+    k x k geometry it takes.  Child process (a device trap must not poison this one); runs only with NEMAR_TEST_RP3=1
+    until the kernel is validated on hardware and made the default."""
+    import json, os, subprocess, sys
+    if not os.environ.get("NEMAR_TEST_RP3"):
+        pytest.skip("resident-patch kernel is opt-in (NEMAR_TC_RP3=1); set NEMAR_TEST_RP3=1 to test it")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = ("import sys, json; sys.path.insert(0, %r); from tests import tc_cases as t\n"
+            "for i in t.RP3_CASES:\n"
+            "    r = t.run_case(i, True); r['bad'] = t.check(r); print('RES ' + json.dumps(r), flush=True)\n") % root
+    env = dict(os.environ, NEMAR_TC_RP3="1")
+    p = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600, env=env)
+    res = [json.loads(l[4:]) for l in p.stdout.splitlines() if l.startswith("RES ")]
+    assert p.returncode == 0 and len(res) == len(tc_cases.RP3_CASES), (p.returncode, p.stderr[-1500:])
+    bad = [r for r in res if r["bad"]]
+    assert not bad, bad
