@@ -33,6 +33,17 @@ CASES = {
                            alpha=1.0, multires_reg=2, multi_resolution=2, ngf=16, ndf=16,
                            extra=["--netG", "resnet_3blocks", "--lambda_smooth", "200.0", "--stn_bilateral_alpha", "1.0",
                                   "--stn_multires_reg", "2", "--multi_resolution", "2", "--ngf", "16", "--ndf", "16"]),
+    # C4 geometry at its real size: 512x512, THREE discriminator scales, bilateral alpha 1.0, three regulariser
+    # levels, resnet_9blocks (reduced widths keep the CPU replay in seconds)
+    "c4_ms3_512": dict(stn_type="unet", n_blocks=9, height=512, width=512, batch=1, steps=2, lambda_smooth=200.0,
+                       alpha=1.0, multires_reg=3, multi_resolution=3, ngf=16, ndf=16,
+                       extra=["--netG", "resnet_9blocks", "--lambda_smooth", "200.0", "--stn_bilateral_alpha", "1.0",
+                              "--stn_multires_reg", "3", "--multi_resolution", "3", "--ngf", "16", "--ndf", "16"]),
+    # ragged edge case: non-square, not a multiple of 128 (the seven floor-pools of the ResUnet go 288 -> 2 and
+    # 384 -> 3 through odd extents 9 and 3; the up path resizes to each skip's size), batch 2
+    "ragged288x384": dict(stn_type="unet", n_blocks=6, height=288, width=384, batch=2, steps=2, lambda_smooth=200.0,
+                          ngf=16, ndf=16,
+                          extra=["--netG", "resnet_6blocks", "--lambda_smooth", "200.0", "--ngf", "16", "--ndf", "16"]),
 }
 
 
@@ -65,7 +76,10 @@ def build_reference(case, NEMARModel, TrainOptions):
 def main():
     NEMARModel, TrainOptions = import_reference()
     torch.manual_seed(0)
+    only = sys.argv[1:]          # optional: generate only the named cases (each case is seeded independently)
     for name, case in CASES.items():
+        if only and name not in only:
+            continue
         cfg = O.OracleConfig(stn_type=case["stn_type"], n_blocks=case["n_blocks"], height=case["height"],
                              width=case["width"], lambda_smooth=case.get("lambda_smooth", 0.0), alpha=case.get("alpha", 0.0),
                              multires_reg=case.get("multires_reg", 1), multi_resolution=case.get("multi_resolution", 1),

@@ -11,6 +11,12 @@ CASE_FLAGS = {
                             multires_reg=2, multi_resolution=2, ngf=16, ndf=16), 1,
                        ["--netG", "resnet_3blocks", "--lambda_smooth", "200.0", "--stn_bilateral_alpha", "1.0",
                         "--stn_multires_reg", "2", "--multi_resolution", "2", "--ngf", "16", "--ndf", "16"]),
+    "c4_ms3_512": (dict(stn_type="unet", n_blocks=9, height=512, width=512, lambda_smooth=200.0, alpha=1.0,
+                        multires_reg=3, multi_resolution=3, ngf=16, ndf=16), 1,
+                   ["--netG", "resnet_9blocks", "--lambda_smooth", "200.0", "--stn_bilateral_alpha", "1.0",
+                    "--stn_multires_reg", "3", "--multi_resolution", "3", "--ngf", "16", "--ndf", "16"]),
+    "ragged288x384": (dict(stn_type="unet", n_blocks=6, height=288, width=384, lambda_smooth=200.0, ngf=16, ndf=16), 2,
+                      ["--netG", "resnet_6blocks", "--lambda_smooth", "200.0", "--ngf", "16", "--ndf", "16"]),
 }
 
 
