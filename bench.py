@@ -193,6 +193,9 @@ def run_engine(args):
         torch.cuda.synchronize()
     if rank != 0:
         if world > 1:
+            if graphed:
+                dist.barrier()          # rank 0 prints its line before any rank leaves (no peer dies under a live rank)
+                torch.cuda.synchronize()
             leave_process_group(graphed)
         return
     # ---- roofline of the dominant kernel (largest share of timed kernel time)
@@ -250,6 +253,8 @@ def run_engine(args):
     print(json.dumps(out))
     sys.stdout.flush()
     if world > 1 and graphed:
+        dist.barrier()
+        torch.cuda.synchronize()
         leave_process_group(graphed)
 
 
