@@ -197,6 +197,10 @@ class NEMARModel(BaseModel):
         if st["failed"]:
             return self._optimize_parameters_eager()
         if st["graph"] is not None:
+            if self.real_A is not self._graph_inputs[0]:
+                # a batch of another shape (e.g. the last, smaller batch of an epoch): set_input could not copy it into
+                # the captured buffers, so this step is launched eagerly
+                return self._optimize_parameters_eager()
             st["graph"].replay()
             L.COUNTERS["launches"] += st["launches"]     # the engine calls one replay stands for
             return
