@@ -203,6 +203,7 @@ class NEMARModel(BaseModel):
                 return self._optimize_parameters_eager()
             st["graph"].replay()
             L.COUNTERS["launches"] += st["launches"]     # the engine calls one replay stands for
+            self.__dict__.update(st["outs"])             # (an eager step in between rebinds loss_* / image attributes)
             return
         if st["eager_steps"] < 3:            # warm-up: lazy initialisation, allocator pools, packed-weight caches
             st["eager_steps"] += 1
@@ -229,6 +230,8 @@ class NEMARModel(BaseModel):
                 self._optimize_parameters_eager()
             st["graph"] = graph
             st["launches"] = L.COUNTERS["launches"] - n0
+            # the tensors a replay writes: losses, images, the regulariser term (attributes bound during the capture)
+            st["outs"] = {k: v for k, v in self.__dict__.items() if torch.is_tensor(v)}
             graph.replay()                    # the capture itself does not execute the step
         except Exception as e:               # noqa: BLE001 - any capture problem => eager launches
             print("CUDA graph capture failed (%s); continuing with eager launches" % str(e).splitlines()[0])
