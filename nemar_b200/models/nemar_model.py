@@ -196,6 +196,9 @@ class NEMARModel(BaseModel):
         st = self.__dict__.setdefault("_graph_state", {"eager_steps": 0, "graph": None, "failed": False})
         if st["failed"]:
             return self._optimize_parameters_eager()
+        lrs = (self.optimizer_TR.param_groups[0]["lr"], self.optimizer_D.param_groups[0]["lr"])
+        if st["graph"] is not None and st.get("lrs") != lrs:
+            st["graph"] = None     # update_learning_rate() ran: the captured Adam launches carry the old rate -> re-capture
         if st["graph"] is not None:
             if self.real_A is not self._graph_inputs[0]:
                 # a batch of another shape (e.g. the last, smaller batch of an epoch): set_input could not copy it into
@@ -229,6 +232,7 @@ class NEMARModel(BaseModel):
                                   capture_error_mode=os.environ.get("NEMAR_GRAPH_CAPTURE_MODE", "thread_local")):
                 self._optimize_parameters_eager()
             st["graph"] = graph
+            st["lrs"] = lrs
             st["launches"] = L.COUNTERS["launches"] - n0
             # the tensors a replay writes: losses, images, the regulariser term (attributes bound during the capture)
             st["outs"] = {k: v for k, v in self.__dict__.items() if torch.is_tensor(v)}
