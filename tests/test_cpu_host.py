@@ -115,3 +115,74 @@ print("rank", rank, "ok")
                        capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
     assert r.stdout.count("ok") == 2
+
+
+def test_cuda_graph_mode_state_machine(monkeypatch):
+    """Host logic of --cuda_graph 1 (NEMARModel._optimize_parameters_graphed) with torch.cuda's graph API mocked: three
+    eager steps, one capture, replays; a batch of another shape runs eagerly and does not leave its outputs bound; a
+    learning-rate change forces a re-capture."""
+    import types
+    from nemar_b200.models import nemar_model as NM
+
+    class FakeGraph:
+        made = []
+
+        def __init__(self):
+            self.replays = 0
+            FakeGraph.made.append(self)
+
+        def replay(self):
+            self.replays += 1
+
+    class Ctx:
+        def __init__(self, *a, **k):
+            pass
+
+        def __enter__(self):
+            return self
+
+        def __exit__(self, *a):
+            return False
+
+    class FakeStream:
+        def wait_stream(self, s):
+            pass
+
+    for name, val in (("CUDAGraph", FakeGraph), ("graph", Ctx), ("Stream", FakeStream), ("stream", Ctx),
+                      ("current_stream", lambda: FakeStream()), ("synchronize", lambda: None)):
+        monkeypatch.setattr(torch.cuda, name, val)
+    m = object.__new__(NM.NEMARModel)
+    m.opt = types.SimpleNamespace(cuda_graph=1, direction="AtoB")
+    m.device = torch.device("cpu")
+    groups = [{"lr": 2e-4}]
+    m.optimizer_TR = types.SimpleNamespace(param_groups=groups)
+    m.optimizer_D = types.SimpleNamespace(param_groups=groups)
+    calls = []
+
+    def eager():
+        calls.append(float(m.real_A.sum()))
+        m.loss_D = torch.tensor(float(len(calls)))     # a fresh tensor per eager step, like the real losses
+    m._optimize_parameters_eager = eager
+    batch = lambda v, n=2: {"A": torch.full((n, 3, 4, 4), float(v)), "B": torch.zeros(n, 3, 4, 4), "A_paths": "", "B_paths": ""}
+    for k in range(3):                                  # eager warm-up steps
+        m.set_input(batch(k))
+        m._optimize_parameters_graphed()
+    assert len(calls) == 3 and not FakeGraph.made
+    m.set_input(batch(3))
+    m._optimize_parameters_graphed()                    # capture (runs the step once under the mocked capture) + replay
+    assert len(calls) == 4 and len(FakeGraph.made) == 1 and FakeGraph.made[0].replays == 1
+    captured_loss = m.loss_D
+    m.set_input(batch(4))
+    m._optimize_parameters_graphed()                    # replay: no eager call, the static input buffer holds the new batch
+    assert len(calls) == 4 and FakeGraph.made[0].replays == 2 and float(m.real_A[0, 0, 0, 0]) == 4.0
+    m.set_input(batch(5, n=1))                          # ragged last batch: cannot be copied into the captured buffers
+    m._optimize_parameters_graphed()
+    assert len(calls) == 5 and calls[-1] == 5.0 * 48 and FakeGraph.made[0].replays == 2
+    assert m.loss_D is not captured_loss
+    m.set_input(batch(6))
+    m._optimize_parameters_graphed()                    # back to replays, and the captured outputs are bound again
+    assert FakeGraph.made[0].replays == 3 and m.loss_D is captured_loss
+    groups[0]["lr"] = 1e-4                              # update_learning_rate()
+    m.set_input(batch(7))
+    m._optimize_parameters_graphed()
+    assert len(FakeGraph.made) == 2 and FakeGraph.made[1].replays == 1 and len(calls) == 6
