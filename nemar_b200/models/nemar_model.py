@@ -194,6 +194,10 @@ class NEMARModel(BaseModel):
 
     def _optimize_parameters_graphed(self):
         st = self.__dict__.setdefault("_graph_state", {"eager_steps": 0, "graph": None, "failed": False})
+        if not st["failed"] and not getattr(self.opt, "no_dropout", True):
+            # dropout draws its mask from a host-side (seed, offset) counter: a replay would repeat the captured mask
+            print("--cuda_graph 1 needs --no_dropout (a replay would repeat one dropout mask); continuing with eager launches")
+            st["failed"] = True
         if st["failed"]:
             return self._optimize_parameters_eager()
         lrs = (self.optimizer_TR.param_groups[0]["lr"], self.optimizer_D.param_groups[0]["lr"])
