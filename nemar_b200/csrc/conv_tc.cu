@@ -20,6 +20,13 @@
 // Warp roles (192 threads): warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane), warps 2-5 = epilogue
 // (TMEM -> registers -> global).  smem ring of STAGES slots guarded by full/empty mbarriers; tcgen05.commit
 // releases slots and publishes the accumulator.
+//
+// Variants in this file (same roles, same barrier protocol):
+//   tc_gather_pair_kernel / tc_wgrad_pair_kernel — CTA pairs (tcgen05 cta_group::2): one M=256 x N=256 MMA per k-step
+//       over the two SMs of a TPC, each CTA staging its own 128 rows of A and its half of B (bit-identical results;
+//       the wgrad pairs are the default for 256-channel layers, NEMAR_TC_PAIR selects);
+//   tc_rp3_kernel — resident-patch kernel for stride-1 k x k layers with <= 64 output channels: persistent CTAs,
+//       weights resident in shared memory, one TMA patch per tile, tap-shifted UMMA windows (opt-in NEMAR_TC_RP3=1).
 #include "common.cuh"
 #include "conv_internal.cuh"
 #include "tc_common.cuh"
