@@ -133,6 +133,7 @@ struct GatherParams {
   int stages;                    // ring depth (<= GatherCfg::STAGES)
   int tpc;                       // destination tiles per CTA (each with its own TMEM accumulator)
   uint32_t tmem_cols;            // power of two >= tpc * accumulator stride
+  int tile0, tile_end;           // tile range of this launch (tc_gather_kernel; set by launch_gather_t)
 };
 
 constexpr int MAX_TPC = 8;
@@ -182,8 +183,8 @@ tc_gather_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // this CTA owns the consecutive destination tiles [t_first, t_first + t_count): one K pipeline runs through all
   // of them while the epilogue warps drain accumulator i during the main loop of tile i + 1
-  const int tiles_total = P.tiles_x * P.tiles_y * P.tiles_n;
-  const int t_first = blockIdx.x * P.tpc;
+  const int tiles_total = P.tile_end;
+  const int t_first = P.tile0 + blockIdx.x * P.tpc;
   const int t_count = (tiles_total - t_first < P.tpc) ? (tiles_total - t_first) : P.tpc;
   const int c0 = blockIdx.y * BN;
   const int ksteps = P.ntaps * P.kchunks;
@@ -696,8 +697,11 @@ static void pick_tile(int dw, int dh, int dn, int& tw, int& th, int& tn, int tot
     }
 }
 
+// tile0 / tile_end: the range of destination tiles this launch covers (tile_end < 0: all of them); force_tpc > 0
+// overrides the tiles-per-CTA heuristic
 template <int BN, int BK, bool F32OUT>
-static int launch_gather_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const GatherParams& P, int ctiles, cudaStream_t s) {
+static int launch_gather_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const GatherParams& P, int ctiles, cudaStream_t s,
+                           int tile0 = 0, int tile_end = -1, int force_tpc = 0) {
   using Cfg = GatherCfg<BN, BK>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -708,7 +712,11 @@ static int launch_gather_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const
   // several destination tiles per CTA when the K loop is short (the fixed cost per CTA — launch, barrier and TMEM
   // set-up, pipeline fill, epilogue — then dominates), as long as the grid still spans >= 4 waves of resident CTAs
   GatherParams Q = P;
-  const int tiles = P.tiles_x * P.tiles_y * P.tiles_n, ksteps = P.ntaps * P.kchunks;
+  const int tiles_all = P.tiles_x * P.tiles_y * P.tiles_n, ksteps = P.ntaps * P.kchunks;
+  Q.tile0 = tile0;
+  Q.tile_end = tile_end < 0 ? tiles_all : tile_end;
+  const int tiles = Q.tile_end - Q.tile0;
+  if (tiles <= 0) return 0;
   // ring depth: the default fills ~96 KB (two CTAs per SM); NEMAR_TC_RING_KB trades depth for residency
   static const int ring_kb = [] { const char* e = getenv("NEMAR_TC_RING_KB"); return e ? atoi(e) : 0; }();
   int stages = Cfg::STAGES;
@@ -732,6 +740,7 @@ static int launch_gather_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const
   static const int waves = [] { const char* e = getenv("NEMAR_TC_TPC_WAVES"); return e ? atoi(e) : 1; }();
   while (tpc > 1 && (long long)((tiles + tpc - 1) / tpc) * ctiles < (long long)waves * occ * sm_count()) tpc >>= 1;
   if (tpc_env > 0) tpc = tpc_env < tpc_limit ? tpc_env : tpc_limit;
+  if (force_tpc > 0) tpc = force_tpc < tpc_limit ? force_tpc : tpc_limit;
   if (tpc < 1) tpc = 1;
   Q.tpc = tpc;
   uint32_t cols = 32;
@@ -744,15 +753,18 @@ static int launch_gather_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const
 }
 
 template <int BN, int BK>
-static int launch_gather_f(const CUtensorMap& a, const CUtensorMap& b, const GatherParams& P, int ct, bool f32, cudaStream_t s) {
-  return f32 ? launch_gather_t<BN, BK, true>(a, b, P, ct, s) : launch_gather_t<BN, BK, false>(a, b, P, ct, s);
+static int launch_gather_f(const CUtensorMap& a, const CUtensorMap& b, const GatherParams& P, int ct, bool f32, cudaStream_t s,
+                           int tile0 = 0, int tile_end = -1, int force_tpc = 0) {
+  return f32 ? launch_gather_t<BN, BK, true>(a, b, P, ct, s, tile0, tile_end, force_tpc)
+             : launch_gather_t<BN, BK, false>(a, b, P, ct, s, tile0, tile_end, force_tpc);
 }
 
 template <int BN>
-static int launch_gather_k(const CUtensorMap& a, const CUtensorMap& b, const GatherParams& P, int ct, int bk, bool f32, cudaStream_t s) {
-  if (bk == 64) return launch_gather_f<BN, 64>(a, b, P, ct, f32, s);
-  if (bk == 32) return launch_gather_f<BN, 32>(a, b, P, ct, f32, s);
-  return launch_gather_f<BN, 16>(a, b, P, ct, f32, s);
+static int launch_gather_k(const CUtensorMap& a, const CUtensorMap& b, const GatherParams& P, int ct, int bk, bool f32, cudaStream_t s,
+                           int tile0 = 0, int tile_end = -1, int force_tpc = 0) {
+  if (bk == 64) return launch_gather_f<BN, 64>(a, b, P, ct, f32, s, tile0, tile_end, force_tpc);
+  if (bk == 32) return launch_gather_f<BN, 32>(a, b, P, ct, f32, s, tile0, tile_end, force_tpc);
+  return launch_gather_f<BN, 16>(a, b, P, ct, f32, s, tile0, tile_end, force_tpc);
 }
 
 // CTA-pair launch: clusters of 2 along x; grid.x = 2 * ceil(tile pairs / tpc)
@@ -986,6 +998,25 @@ int tc_gather_gemm(const nemar_tensor* src_in, const nemar_tensor* dst_in, const
       rc = launch_gather_pair(tmA, tmB, P, ctiles, s);
       if (rc) return rc;
       continue;
+    }
+    // Wave-tail split (opt-in NEMAR_TC_TAIL=1): 128x128 tile-units over 2 CTAs/SM leave a last, partly filled wave that
+    // costs a whole unit-time (1024 units / 296 slots = 3.46 -> 4).  Run the whole waves as they are (one tile per CTA)
+    // and the remaining tiles as half-width (BN = 64) units in a second launch of the same kernel template.
+    static const int tail_env = [] { const char* e = getenv("NEMAR_TC_TAIL"); return e ? atoi(e) : 0; }();
+    if (tail_env && BN == 128 && BK == 64 && !f32 && !P.stats) {
+      const int tiles = P.tiles_x * P.tiles_y * P.tiles_n, slots = 2 * sm_count();
+      const int units = tiles * ctiles, full = units / slots * slots, rem = units - full;
+      const int tiles_main = full / ctiles;
+      if (full > 0 && rem > 0 && 2 * (tiles - tiles_main) * ctiles <= slots + slots / 8) {
+        CUtensorMap tmB64;
+        rc = make_w_map(&tmB64, wp, dst.c, taps_total * src.c, BK, 64);
+        if (rc) return rc;
+        rc = launch_gather_k<128>(tmA, tmB, P, ctiles, BK, f32, s, 0, tiles_main, 1);
+        if (rc) return rc;
+        rc = launch_gather_k<64>(tmA, tmB64, P, dst.c / 64, BK, f32, s, tiles_main, tiles, 1);
+        if (rc) return rc;
+        continue;
+      }
     }
     switch (BN) {
       case 256: rc = launch_gather_t<256, 64, false>(tmA, tmB, P, ctiles, s); break;
