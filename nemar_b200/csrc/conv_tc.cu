@@ -999,25 +999,6 @@ int tc_gather_gemm(const nemar_tensor* src_in, const nemar_tensor* dst_in, const
       if (rc) return rc;
       continue;
     }
-    // Wave-tail split (opt-in NEMAR_TC_TAIL=1): 128x128 tile-units over 2 CTAs/SM leave a last, partly filled wave that
-    // costs a whole unit-time (1024 units / 296 slots = 3.46 -> 4).  Run the whole waves as they are (one tile per CTA)
-    // and the remaining tiles as half-width (BN = 64) units in a second launch of the same kernel template.
-    static const int tail_env = [] { const char* e = getenv("NEMAR_TC_TAIL"); return e ? atoi(e) : 0; }();
-    if (tail_env && BN == 128 && BK == 64 && !f32 && !P.stats) {
-      const int tiles = P.tiles_x * P.tiles_y * P.tiles_n, slots = 2 * sm_count();
-      const int units = tiles * ctiles, full = units / slots * slots, rem = units - full;
-      const int tiles_main = full / ctiles;
-      if (full > 0 && rem > 0 && 2 * (tiles - tiles_main) * ctiles <= slots + slots / 8) {
-        CUtensorMap tmB64;
-        rc = make_w_map(&tmB64, wp, dst.c, taps_total * src.c, BK, 64);
-        if (rc) return rc;
-        rc = launch_gather_k<128>(tmA, tmB, P, ctiles, BK, f32, s, 0, tiles_main, 1);
-        if (rc) return rc;
-        rc = launch_gather_k<64>(tmA, tmB64, P, dst.c / 64, BK, f32, s, tiles_main, tiles, 1);
-        if (rc) return rc;
-        continue;
-      }
-    }
     switch (BN) {
       case 256: rc = launch_gather_t<256, 64, false>(tmA, tmB, P, ctiles, s); break;
       case 128: rc = launch_gather_k<128>(tmA, tmB, P, ctiles, BK, f32, s); break;

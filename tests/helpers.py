@@ -60,3 +60,15 @@ def run_engine_steps(model, A, B, steps):
         losses.append(list(model.get_current_losses().values()))
     torch.cuda.synchronize()
     return losses
+
+
+def structured_batch(n, h, w, seed=5, shift=4):
+    """Smooth random images in [-1, 1]; B = another intensity mapping of A, shifted by `shift` pixels along x (a
+    registration problem with a known answer, unlike the white-noise batches of the step goldens)."""
+    g = torch.Generator().manual_seed(seed)
+    low = torch.rand((n, 3, h // 8, w // 8), generator=g) * 2 - 1
+    A = torch.nn.functional.interpolate(low, (h, w), mode="bicubic", align_corners=False).clamp(-1, 1)
+    A = (A + 0.05 * (torch.rand((n, 3, h, w), generator=g) * 2 - 1)).clamp(-1, 1)
+    mapped = torch.tanh(1.5 * A.flip(1)) * 0.9
+    B = torch.roll(mapped, shifts=shift, dims=3)
+    return A, B

@@ -13,19 +13,10 @@ def test_tc_engine_matches_generic(idx):
     assert not bad, "%s: out of tolerance %s in %s" % (res["case"], bad, res)
 
 
-def _pair_is_default():
-    from nemar_b200.engine import lib as L
-    import ctypes as C
-    return L.lib().nemar_conv2d_set_option(C.c_char_p(b"pair"), C.c_int(-1)) > 0
-
-
 def test_tc_pair_mode_matches_generic():
     """CTA-pair kernels (tcgen05 cta_group::2) on every geometry they take.  Runs in a child process with
-    NEMAR_TC_PAIR=1 (a device trap must not poison this process's context); until the pair mode is the engine's
-    default the test runs only when NEMAR_TEST_PAIR=1."""
+    NEMAR_TC_PAIR=1 (a device trap must not poison this process's context)."""
     import json, os, subprocess, sys
-    if not (os.environ.get("NEMAR_TEST_PAIR") or _pair_is_default()):
-        pytest.skip("pair mode is opt-in (NEMAR_TC_PAIR=1); set NEMAR_TEST_PAIR=1 to test it")
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     code = ("import sys, json; sys.path.insert(0, %r); from tests import tc_cases as t\n"
             "for i in t.PAIR_CASES:\n"
@@ -40,11 +31,9 @@ def test_tc_pair_mode_matches_generic():
 
 def test_tc_resident_patch_mode_matches_generic():
     """Resident-patch kernel (tap-shifted UMMA windows over one TMA patch; opt-in NEMAR_TC_RP3=1) on every stride-1
-    k x k geometry it takes.  Child process (a device trap must not poison this one); runs only with NEMAR_TEST_RP3=1
-    until the kernel is validated on hardware and made the default."""
+    k x k geometry it takes.  Child process (a device trap must not poison this one).  First green on a B200 in
+    round 2 (profiles/r02_rp3_cases.txt)."""
     import json, os, subprocess, sys
-    if not os.environ.get("NEMAR_TEST_RP3"):
-        pytest.skip("resident-patch kernel is opt-in (NEMAR_TC_RP3=1); set NEMAR_TEST_RP3=1 to test it")
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     code = ("import sys, json; sys.path.insert(0, %r); from tests import tc_cases as t\n"
             "for i in t.RP3_CASES:\n"

@@ -1,7 +1,7 @@
 """Engine vs the reference's golden vectors at C4's real geometry (512x512, three discriminator scales, bilateral
 alpha, three regulariser levels) and on a ragged 288x384 input (odd intermediate extents, batch 2).  The CPU oracle is
-pinned on the same vectors in tests/test_oracle_golden.py.  These two cases were added after the round's GPU budget
-was spent: they run when NEMAR_TEST_UNVALIDATED=1 and become unconditional once they have passed on a B200."""
+pinned on the same vectors in tests/test_oracle_golden.py.  First green on a B200 in round 2 (8 passed,
+profiles/r02_golden_sizes.txt); unconditional since."""
 import os
 
 import numpy as np
@@ -12,11 +12,6 @@ pytestmark = pytest.mark.gpu
 from tests import helpers as H  # noqa: E402
 from tests.test_gpu_model import GOLD, _check_traj  # noqa: E402
 
-pending = pytest.mark.skipif(not os.environ.get("NEMAR_TEST_UNVALIDATED"),
-                             reason="added without GPU budget left; set NEMAR_TEST_UNVALIDATED=1")
-
-
-@pending
 @pytest.mark.parametrize("name", ["c4_ms3_512", "ragged288x384"])
 def test_training_step_fp32_vs_reference_golden_sizes(name):
     g = np.load(os.path.join(GOLD, name + ".npz"))
@@ -25,7 +20,6 @@ def test_training_step_fp32_vs_reference_golden_sizes(name):
     _check_traj(losses, g["losses"], 3e-4, 2e-5)
 
 
-@pending
 @pytest.mark.parametrize("name", ["c4_ms3_512", "ragged288x384"])
 @pytest.mark.parametrize("conv_engine", ["generic", "auto"])
 def test_training_step_bf16_vs_reference_golden_sizes(name, conv_engine):
@@ -35,7 +29,6 @@ def test_training_step_bf16_vs_reference_golden_sizes(name, conv_engine):
     _check_traj(losses, g["losses"], 4e-2, 2e-2)
 
 
-@pending
 @pytest.mark.parametrize("name", ["c4_ms3_512", "ragged288x384"])
 def test_first_step_images_fp32_vs_reference_golden_sizes(name):
     g = np.load(os.path.join(GOLD, name + ".npz"))
