@@ -2,6 +2,7 @@
 resolves to class FooDataset in nemar_b200/data/foo_dataset.py; items are dicts
 {'A': CxHxW float in [-1,1], 'B': ..., 'A_paths': str, 'B_paths': str}."""
 import importlib
+import os
 
 import torch.utils.data
 
@@ -30,9 +31,17 @@ class CustomDatasetDataLoader:
         self.opt = opt
         self.dataset = find_dataset_using_name(opt.dataset_mode)(opt)
         print("dataset [%s] was created" % type(self.dataset).__name__)
+        # multi-rank jobs: every rank iterates the SAME global batches (train.py keeps its shard), so the shuffle must
+        # not depend on how much of the default RNG a rank happened to consume, and a short last batch is dropped
+        # (an uneven shard would drop samples silently or stall the other ranks' all-reduce)
+        world = int(os.environ.get("WORLD_SIZE", "1"))
+        gen = None
+        if world > 1:
+            gen = torch.Generator()
+            gen.manual_seed(int(getattr(opt, "data_seed", 0)))
         self.dataloader = torch.utils.data.DataLoader(self.dataset, batch_size=opt.batch_size,
                                                       shuffle=not opt.serial_batches, num_workers=int(opt.num_threads),
-                                                      pin_memory=bool(opt.gpu_ids))
+                                                      pin_memory=bool(opt.gpu_ids), drop_last=world > 1, generator=gen)
 
     def load_data(self):
         return self

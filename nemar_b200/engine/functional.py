@@ -34,6 +34,8 @@ def _deliver(param, grad):
     capturable in a CUDA graph).  Otherwise return the gradient for autograd to store."""
     if grad is None:
         return None
+    if param is not None and not param.requires_grad:
+        return None                      # frozen by set_requires_grad(False): nothing may reach its bucket
     if param is not None and param.is_leaf and param.grad is not None and param.grad.shape == grad.shape:
         param.grad.add_(grad)
         return None
@@ -213,7 +215,9 @@ class PackedWeights:
     def get(self, weight, bias, cfg, dtype, cin_p):
         key = (dtype, cin_p, cfg.cout_p)
         ent = self.cache.get(key)
-        stamp = (weights_epoch(), weight.data_ptr())
+        # (epoch bumped by the engine's own optimizer / loaders; _version catches any other in-place write — a foreign
+        #  load_state_dict, an EMA, a manual weight.copy_)
+        stamp = (weights_epoch(), weight.data_ptr(), weight._version, bias._version if bias is not None else 0)
         if ent is None or ent[0] != stamp:
             k2 = cfg.k * cfg.k
             wf = torch.empty(cfg.cout_p * k2 * cin_p, dtype=dtype, device=weight.device)

@@ -19,10 +19,30 @@ def init_process_group_from_env(backend=None):
         os.environ.setdefault("MASTER_PORT", "29500")
         if backend is None:
             backend = "nccl" if torch.cuda.is_available() else "gloo"
-        if backend == "nccl":
-            torch.cuda.set_device(local)
+        # the CUDA device is the caller's choice (BaseOptions.parse maps LOCAL_RANK through --gpu_ids; bench.py and the
+        # tests call torch.cuda.set_device themselves): NCCL binds to whatever device is current at the first collective
         dist.init_process_group(backend=backend, rank=rank, world_size=world)
     return world, rank, local
+
+
+def world_size():
+    return dist.get_world_size() if dist.is_initialized() else 1
+
+
+def broadcast_buffers(tensors, src=0):
+    """Make every rank start from rank `src`'s values (flat parameter buffers after construction / a checkpoint load):
+    replicas then stay bit-synchronous because every rank applies the same averaged gradient."""
+    if world_size() > 1:
+        for t in tensors:
+            dist.broadcast(t, src=src)
+
+
+def check_global_batch(batch_size):
+    """A global batch must split evenly: an uneven last shard would silently drop samples or hang the all-reduce."""
+    w = world_size()
+    if batch_size % w != 0:
+        raise ValueError("--batch_size %d is not divisible by the %d ranks of this job" % (batch_size, w))
+    return batch_size // w
 
 
 def shard_batch(t, rank, world):
@@ -44,3 +64,20 @@ class BucketAllReduce:
             self.calls += 1
             return 1.0 / dist.get_world_size(self.group)
         return 1.0
+
+
+def shutdown(graph_mode=False):
+    """Leave a multi-rank job.  After a captured step with NCCL all-reduces inside, destroy_process_group() never
+    returns (measured at 2 ranks, torch 2.11 / NCCL 2.28): such jobs synchronise, meet at a barrier and exit the
+    process directly; everything else tears the group down normally."""
+    if not dist.is_initialized():
+        return
+    if torch.cuda.is_available():
+        torch.cuda.synchronize()
+    dist.barrier()
+    if graph_mode and dist.get_backend() == "nccl":
+        import sys
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
+    dist.destroy_process_group()

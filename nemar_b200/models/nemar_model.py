@@ -94,6 +94,8 @@ class NEMARModel(BaseModel):
         self.optimizer_TR.grad_hook = hook
         self.optimizer_D.grad_hook = hook
         self.allreduce = hook
+        # replicas must start identical whatever each process's RNG did before this point
+        parallel.broadcast_buffers([self.optimizer_TR.flat_p, self.optimizer_D.flat_p])
 
     def set_input(self, input):
         AtoB = self.opt.direction == "AtoB"
@@ -212,6 +214,10 @@ class NEMARModel(BaseModel):
             L.COUNTERS["launches"] += st["launches"]     # the engine calls one replay stands for
             self.__dict__.update(st["outs"])             # (an eager step in between rebinds loss_* / image attributes)
             return
+        if st["eager_steps"] >= 3 and self.real_A is not self._graph_inputs[0]:
+            # the batch of the capture step has another shape (the short last batch of a small dataset): set_input bound
+            # temporaries, and a graph captured now would read THEM forever.  Run it eagerly, capture on a later step.
+            return self._optimize_parameters_eager()
         if st["eager_steps"] < 3:            # warm-up: lazy initialisation, allocator pools, packed-weight caches
             st["eager_steps"] += 1
             if self.__dict__.get("_graph_inputs") is None:

@@ -168,6 +168,12 @@ def test_cuda_graph_mode_state_machine(monkeypatch):
         m.set_input(batch(k))
         m._optimize_parameters_graphed()
     assert len(calls) == 3 and not FakeGraph.made
+    # the step that would capture sees a ragged batch (short last batch of a small dataset): set_input bound temporaries,
+    # so it must run eagerly and leave the capture to a later full-size step (else the graph reads stale buffers forever)
+    m.set_input(batch(9, n=1))
+    m._optimize_parameters_graphed()
+    assert len(calls) == 4 and calls[-1] == 9.0 * 48 and not FakeGraph.made
+    calls.pop()
     m.set_input(batch(3))
     m._optimize_parameters_graphed()                    # capture (runs the step once under the mocked capture) + replay
     assert len(calls) == 4 and len(FakeGraph.made) == 1 and FakeGraph.made[0].replays == 1

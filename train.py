@@ -39,6 +39,7 @@ def main():
 
     opt = TrainOptions().parse()
     world, rank, _ = parallel.init_process_group_from_env()
+    parallel.check_global_batch(opt.batch_size)
     dataset = create_dataset(opt)
     dataset_size = len(dataset)
     print("The number of training images = %d" % dataset_size)
@@ -77,6 +78,7 @@ def main():
             model.save_networks("latest")
             model.save_networks(epoch)
         print("End of epoch %d / %d \t Time Taken: %d sec" % (epoch, opt.niter + opt.niter_decay, time.time() - epoch_start_time))
+    parallel.shutdown(graph_mode=bool(getattr(opt, "cuda_graph", 0)))
 
 
 if __name__ == "__main__":
