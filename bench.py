@@ -26,6 +26,16 @@ HW = 256
 PER_GPU_BATCH = 16
 CONV_GFLOP_PER_SAMPLE = 724.72     # algorithmic conv FLOPs (2*MAC, fwd+bwd) per paired sample
 WORKLOAD = "C2: 256x256 synthetic A/B, unet STN cfg A + resnet_9blocks + PatchGAN, lsgan, no_dropout, batch 16/GPU"
+# BASELINE.json configs: name -> (size, per-GPU batch, extra flags, conv GFLOP per paired sample, label)
+WORKLOADS = {
+    "C2": dict(size=256, batch=16, multi_resolution=1, lambda_smooth=0.0, alpha=0.0, multires_reg=1, gflop=724.72, label=WORKLOAD),
+    "C4": dict(size=512, batch=8, multi_resolution=3, lambda_smooth=200.0, alpha=1.0, multires_reg=3, gflop=3008.06,
+               label="C4: 512x512 synthetic A/B, unet STN + resnet_9blocks, 3-scale PatchGAN (--multi_resolution 3), bilateral "
+                     "smoothness (--lambda_smooth 200 --stn_bilateral_alpha 1.0 --stn_multires_reg 3), lsgan, no_dropout, batch 8/GPU"),
+    "C5": dict(size=1024, batch=4, multi_resolution=1, lambda_smooth=0.0, alpha=0.0, multires_reg=1, gflop=11636.88,
+               label="C5: 1024x1024 synthetic A/B, unet STN (dense deformation field) + resnet_9blocks + PatchGAN, lsgan, "
+                     "no_dropout, batch 4/GPU"),
+}
 
 
 def load_peaks():
@@ -125,15 +135,20 @@ def run_engine(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    from nemar_b200.data.prefetch import DevicePrefetcher
+
     def timed(batch, steps, read_loss):
+        # e2e (read_loss): host batches go through the product's own input pipeline — every step's inputs are copied
+        # from pinned host memory inside the timed region (side stream, overlapped with the previous step)
+        feed = DevicePrefetcher([batch] * steps, dev) if read_loss else [batch] * steps
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for _ in range(steps):
-            model.set_input(batch)
+        for data in feed:
+            model.set_input(data)
             model.optimize_parameters()
             if read_loss:
-                _ = float(model.loss_D)        # device -> host read of the step's result
+                _ = float(model.loss_D.detach())        # device -> host read of the step's result
         e1.record()
         barrier()
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
@@ -149,7 +164,8 @@ def run_engine(args):
     if not graph_wanted:
         opt.cuda_graph = 0
     # graph mode: three eager steps on the capture stream, the capture (+ first replay), then replays
-    for _ in range(args.warmup if args.profile else max(args.warmup, 3) + (4 if graph_wanted else 0)):
+    n_warm = args.warmup if args.profile else max(args.warmup, 3) + (4 if graph_wanted else 0)
+    for _ in range(n_warm):
         step()
     torch.cuda.synchronize()
 
@@ -200,19 +216,14 @@ def run_engine(args):
         return
     # ---- roofline of the dominant kernel (largest share of timed kernel time)
     roof = None
-    ncu_traffic = None
-    try:      # dram__bytes_read+write per launch of the dominant kernel from the committed `ncu --set full` capture
-        prof = json.load(open(os.path.join(ROOT, "profiles", "r01_dominant_kernel_ncu.json")))["per_launch"]
-        ncu_traffic = round((prof["dram__bytes_read_MB"] + prof["dram__bytes_write_MB"]) * 1e6)
-    except Exception:
-        pass
+    ncu_traffic, traffic_note = dominant_kernel_traffic()
     if kstats:
         name, st = max(kstats.items(), key=lambda kv: kv[1]["ms"])
         tf = st["flops"] / (st["ms"] / 1e3) / 1e12 if st["ms"] > 0 else 0.0
         tot_ms = sum(v["ms"] for v in kstats.values())
         roof = {"bound": "tensor", "kernel": name, "achieved": round(tf, 2), "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
                 "frac": round(tf / peaks["tf_sustained"], 4), "traffic": ncu_traffic,
-                "traffic_note": "bytes/launch of the 256->256 k3 instance (algorithmic 70.3 MB; the output stays in L2)", "peak_source": peaks["source"] + ", sustained",
+                "traffic_note": traffic_note, "peak_source": peaks["source"] + ", sustained",
                 "timed_in": roofline_pass, "launches": st["n"], "avg_launch_ms": round(st["ms"] / max(st["n"], 1), 4),
                 "share_of_timed_kernels": round(st["ms"] / max(tot_ms, 1e-9), 4),
                 "by_kernel": {k: {"ms": round(v["ms"], 3), "n": v["n"],
@@ -223,13 +234,16 @@ def run_engine(args):
         roof = {"bound": "tensor", "achieved": None, "peak": peaks["tf_sustained"], "unit": "TFLOP/s", "frac": None, "traffic": ncu_traffic,
                 "note": "per-kernel figures are timed at N = 1 (eager pass after the replayed region); a multi-rank run replays "
                         "the captured step only — see conv_roofline_frac_whole_step for the whole-step figure at this N"}
-    conv_frac = value * CONV_GFLOP_PER_SAMPLE * 1e9 / (world * peaks["tf_sustained"] * 1e12) if args.size == HW else None
-    out = {"metric": "paired 256x256 samples/sec", "value": round(value, 3), "unit": "samples/s", "n_gpus": world,
-           "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": round(ms / args.steps, 3),
+    gflop = args.gflop
+    conv_frac = value * gflop * 1e9 / (world * peaks["tf_sustained"] * 1e12) if gflop else None
+    out = {"metric": "paired %dx%d samples/sec" % (args.size, args.size), "value": round(value, 3), "unit": "samples/s", "n_gpus": world,
+           "steps": args.steps, "warmup": n_warm, "ms_per_step": round(ms / args.steps, 3),
            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
-           "config": {"workload": WORKLOAD if (args.size == HW and args.batch == PER_GPU_BATCH) else
+           "config": {"workload": args.label if args.label else
                       "%dx%d unet STN + resnet_9blocks, batch %d/GPU, multi_resolution %d, lambda_smooth %g alpha %g" % (
                           args.size, args.size, args.batch, args.multi_resolution, args.lambda_smooth, args.alpha),
+                      "warmup_note": "%d warm-up steps%s" % (n_warm, " (3 eager + the capture step + replays)" if graph_wanted else ""),
+                      "conv_gflop_per_sample": gflop,
                       "global_batch": global_batch, "parallelism": "dp%d" % world, "conv_engine": args.conv_engine,
                       "l2": "inputs larger than L2: a step streams several GB of activations, no flush needed",
                       "cuda_graph": graphed, "batch_d": int(getattr(opt, "batch_d", 1)),
@@ -242,9 +256,14 @@ def run_engine(args):
            "roofline": roof}
     if world == 1 and not args.no_cpu_baseline:
         try:
-            out["cpu_baseline"] = cpu_baseline(args.size, budget_s=15.0)
+            out["cpu_baseline"] = cpu_baseline(args, budget_s=15.0)
         except Exception as e:      # noqa: BLE001
             out["cpu_baseline"] = {"error": repr(e)}
+    if world == 1 and args.torch_gpu_reference:
+        try:
+            out["torch_gpu_reference"] = torch_gpu_reference(args, dev)
+        except Exception as e:      # noqa: BLE001
+            out["torch_gpu_reference"] = {"error": repr(e)[:300]}
     if args.grid_sample_bench:
         try:
             out["grid_sample"] = grid_sample_bench(dev, peaks)
@@ -256,6 +275,23 @@ def run_engine(args):
         dist.barrier()
         torch.cuda.synchronize()
         leave_process_group(graphed)
+
+
+def dominant_kernel_traffic():
+    """dram__bytes_read + dram__bytes_write per launch of the dominant conv instance (256->256 k3) from the committed
+    `ncu --set full` summary — only when that capture was taken on the kernel sources this library was built from
+    (digest of nemar_b200/csrc, written by nemar_b200/build.py); otherwise null."""
+    try:
+        prof = json.load(open(os.path.join(ROOT, "profiles", "dominant_kernel_ncu.json")))
+        built = open(os.path.join(ROOT, "nemar_b200", "build", "stamp")).read().strip()
+        if prof.get("lib_digest") != built:
+            return None, "no ncu capture of this build (profiles/dominant_kernel_ncu.json was taken on digest %s...)" % str(prof.get("lib_digest"))[:12]
+        pl = prof["per_launch"]
+        return (round((pl["dram__bytes_read_MB"] + pl["dram__bytes_write_MB"]) * 1e6),
+                "dram bytes/launch of the 256->256 k3 fprop instance from %s (algorithmic 70.3 MB: the bf16 output stays in "
+                "the 126 MB L2 and is consumed from there)" % prof.get("file", "profiles/dominant_kernel_ncu.json"))
+    except Exception:
+        return None, "no ncu capture of this build committed"
 
 
 def leave_process_group(graphed):
@@ -271,34 +307,31 @@ def leave_process_group(graphed):
 
 
 def pick_cpu_threads():
-    """Host threads for the CPU arm: all the cores this process may use, unless fewer threads are faster (cgroup
-    quotas / SMT oversubscription make MKL-DNN collapse at 128 threads on the GPU boxes) — short calibration."""
+    """Host threads for the CPU arm — ONE deterministic rule: min(cores this process may use, 32).  The oracle's ATen /
+    oneDNN convolutions at batch 2 stop scaling there on the GPU boxes (16 threads 2.2 samples/s, 32 threads 3.6,
+    128 threads collapse); round 1's timing-based calibration flipped between 16 and 32 from run to run."""
     try:
         avail = len(os.sched_getaffinity(0))
     except AttributeError:
         avail = os.cpu_count() or 1
-    x = torch.randn(2, 64, 128, 128)
-    w = torch.randn(64, 64, 3, 3)
-    best, best_t = 1, float("inf")
-    cands = sorted({c for c in (8, 16, 32, 64, avail) if c <= avail} | {min(avail, 8)})
-    for c in cands:
-        torch.set_num_threads(c)
-        torch.nn.functional.conv2d(x, w, padding=1)
-        t0 = time.time()
-        for _ in range(3):
-            torch.nn.functional.conv2d(x, w, padding=1)
-        dt = time.time() - t0
-        if dt < best_t:
-            best, best_t = c, dt
-    torch.set_num_threads(best)
-    return best
+    n = max(1, min(avail, 32))
+    torch.set_num_threads(n)
+    return n
 
 
-def cpu_baseline(size, budget_s, batch=2, stn_type="unet", n_blocks=9):
+def oracle_cfg(args):
+    from oracle import nemar_oracle as O
+    return O.OracleConfig(stn_type="unet", n_blocks=9, height=args.size, width=args.size, lambda_smooth=args.lambda_smooth,
+                          alpha=args.alpha, multires_reg=args.multires_reg, multi_resolution=args.multi_resolution)
+
+
+def cpu_baseline(args, budget_s, batch=2, n_blocks=9):
     """The oracle port of the reference's CPU path, timed on this box's host cores on a bounded sample."""
     from oracle import nemar_oracle as O
     pick_cpu_threads()
-    cfg = O.OracleConfig(stn_type=stn_type, n_blocks=n_blocks, height=size, width=size)
+    size = args.size
+    batch = 1 if size >= 1024 else batch
+    cfg = oracle_cfg(args)
     T, R, Ds = O.make_states(cfg, seed=0, live_head=False)
     A, B = O.synthetic_batch(batch, size, size, seed=1)
     st = O.OracleStep(cfg, T, R, Ds)
@@ -313,6 +346,46 @@ def cpu_baseline(size, budget_s, batch=2, stn_type="unet", n_blocks=9):
                       "(the reference's own ATen path restated in oracle/nemar_oracle.py)" % (n, size, size, n_blocks, batch)}
 
 
+def torch_gpu_reference(args, dev, steps=5):
+    """Informational: the reference's algorithm as eager PyTorch on the SAME B200 — fp32
+    storage, ATen / cuDNN sm_100 kernels, what a NeMAR user gets from `--gpu_ids 0` today.  /root/reference does not
+    exist on the GPU box, so this runs the golden-pinned restatement (oracle/nemar_oracle.py: the same torch ops on
+    state dicts) with every tensor on the device; same workload and batch as the engine line."""
+    from collections import OrderedDict
+    from oracle import nemar_oracle as O
+    cfg = O.OracleConfig(stn_type="unet", n_blocks=9, height=args.size, width=args.size, lambda_smooth=args.lambda_smooth,
+                         alpha=args.alpha, multires_reg=args.multires_reg, multi_resolution=args.multi_resolution)
+    T, R, Ds = O.make_states(cfg, seed=0, live_head=False)
+    mv = lambda sd: OrderedDict((k, v.to(dev)) for k, v in sd.items())
+    res = {}
+    A, B = O.synthetic_batch(args.batch, args.size, args.size, seed=1)
+    A, B = A.to(dev), B.to(dev)
+    for name, tf32 in (("fp32", False), ("tf32", True)):
+        torch.backends.cudnn.allow_tf32 = tf32
+        torch.backends.cuda.matmul.allow_tf32 = tf32
+        torch.backends.cudnn.benchmark = True           # the reference sets it (models/base_model.py:39)
+        st = O.OracleStep(cfg, mv(T), mv(R), [mv(d) for d in Ds])
+        for _ in range(3):
+            st.step(A, B)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            st.step(A, B)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        res[name] = {"value": round(args.batch / (ms / 1e3), 2), "unit": "samples/s", "ms_per_step": round(ms, 2)}
+        del st
+        torch.cuda.empty_cache()
+    torch.backends.cudnn.allow_tf32 = True
+    res["kind"] = "port"
+    res["what"] = ("the reference's optimize_parameters restated in torch (oracle/nemar_oracle.py, golden-pinned to the reference) "
+                   "run eagerly on cuda:0, batch %d: ATen/cuDNN kernels, fp32 storage; 'tf32' = same with TF32 tensor-core math "
+                   "allowed.  Each step ends with the loss read-back the reference's logging does" % args.batch)
+    return res
+
+
 def run_reference(args):
     """`--impl reference`: the reference's own CPU implementation of the path (oracle port), all host threads.
     Under torchrun only rank 0 works."""
@@ -320,26 +393,26 @@ def run_reference(args):
         return
     from oracle import nemar_oracle as O
     pick_cpu_threads()
-    batch = 2
-    cfg = O.OracleConfig(stn_type="unet", n_blocks=9, height=args.size, width=args.size)
+    batch = 1 if args.size >= 1024 else 2
+    cfg = oracle_cfg(args)
     T, R, Ds = O.make_states(cfg, seed=0, live_head=False)
     A, B = O.synthetic_batch(batch, args.size, args.size, seed=1)
     st = O.OracleStep(cfg, T, R, Ds)
     for _ in range(max(1, min(args.warmup, 2))):
         st.step(A, B)
-    steps = max(1, min(args.steps, 10))
+    steps = max(1, min(args.steps, 10 if args.size <= 256 else 3))
     t0 = time.time()
     for _ in range(steps):
         st.step(A, B)
     dt = time.time() - t0
     value = batch * steps / dt
-    sample = "each step = one optimize_parameters at batch %d (bounded sample of the batch-16 workload; CPU samples/s is " \
-             "batch-insensitive), fp32, %d threads" % (batch, torch.get_num_threads())
-    print(json.dumps({"impl": "reference", "metric": "paired 256x256 samples/sec", "value": round(value, 4), "unit": "samples/s",
+    sample = "each step = one optimize_parameters at batch %d (bounded sample of the batch-%d workload; CPU samples/s is " \
+             "batch-insensitive), fp32, %d threads" % (batch, args.batch, torch.get_num_threads())
+    print(json.dumps({"impl": "reference", "metric": "paired %dx%d samples/sec" % (args.size, args.size), "value": round(value, 4), "unit": "samples/s",
                       "n_gpus": args.gpus, "steps": steps, "warmup": max(1, min(args.warmup, 2)),
                       "ms_per_step": round(dt / steps * 1e3, 2), "higher_is_better": True, "scaling": "weak",
                       "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
-                      "config": {"workload": WORKLOAD, "global_batch": batch, "parallelism": "cpu"},
+                      "config": {"workload": args.label or "%dx%d" % (args.size, args.size), "global_batch": batch, "parallelism": "cpu"},
                       "cpu_baseline": {"value": round(value, 4), "unit": "samples/s", "cores": torch.get_num_threads(),
                                        "kind": "port", "sample": sample},
                       "e2e": {"value": round(value, 4), "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
@@ -397,15 +470,21 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", type=str, default="b200", choices=["b200", "reference"])
-    ap.add_argument("--batch", type=int, default=PER_GPU_BATCH, help="paired samples per GPU")
-    ap.add_argument("--size", type=int, default=HW)
+    ap.add_argument("--workload", type=str, default="C2", choices=sorted(WORKLOADS),
+                    help="BASELINE.json configuration: C2 (256^2, the metric's config; default), C4 (512^2, 3-scale D, bilateral), "
+                         "C5 (1024^2); --batch/--size/... override its fields")
+    ap.add_argument("--batch", type=int, default=None, help="paired samples per GPU")
+    ap.add_argument("--size", type=int, default=None)
     ap.add_argument("--precision", type=str, default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--conv_engine", type=str, default="auto", choices=["auto", "generic"])
     ap.add_argument("--no_cpu_baseline", action="store_true")
-    ap.add_argument("--multi_resolution", type=int, default=1, help="discriminator scales (C4: 3)")
-    ap.add_argument("--lambda_smooth", type=float, default=0.0, help="STN regulariser weight (C4: 200)")
-    ap.add_argument("--alpha", type=float, default=0.0, help="bilateral alpha of the smoothness term (C4: 1.0)")
-    ap.add_argument("--multires_reg", type=int, default=1)
+    ap.add_argument("--multi_resolution", type=int, default=None, help="discriminator scales (C4: 3)")
+    ap.add_argument("--lambda_smooth", type=float, default=None, help="STN regulariser weight (C4: 200)")
+    ap.add_argument("--alpha", type=float, default=None, help="bilateral alpha of the smoothness term (C4: 1.0)")
+    ap.add_argument("--multires_reg", type=int, default=None)
+    ap.add_argument("--torch_gpu_reference", type=int, default=1,
+                    help="1: also time the reference's algorithm as eager fp32 PyTorch on cuda:0 (ATen/cuDNN kernels) — "
+                         "the informal 'reference on Blackwell' bar of BASELINE.md section 3 item 5 (N = 1 only)")
     ap.add_argument("--batch_d", type=int, default=-1, help="-1: the engine's default; 0/1: one discriminator pass per (A, B) pair / per phase")
     ap.add_argument("--cuda_graph", type=int, default=1,
                     help="1 (default): the model captures optimize_parameters in a CUDA graph (its --cuda_graph 1 flag) and the "
@@ -416,6 +495,15 @@ def main():
     ap.add_argument("--profile", action="store_true", help="for ncu runs: honour --warmup below 3 (numbers printed under a "
                                                            "profiler are never bench values)")
     args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
+    overridden = False
+    for k in ("size", "batch", "multi_resolution", "lambda_smooth", "alpha", "multires_reg"):
+        if getattr(args, k) is None:
+            setattr(args, k, wl[k])
+        elif getattr(args, k) != wl[k]:
+            overridden = True
+    args.label = None if overridden else wl["label"]
+    args.gflop = wl["gflop"] if (args.size == wl["size"] and args.multi_resolution == wl["multi_resolution"]) else None
     if args.impl == "reference":
         run_reference(args)
     else:

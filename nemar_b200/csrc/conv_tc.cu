@@ -153,6 +153,83 @@ __device__ __forceinline__ void warp_transpose_sum(float (&a)[32], int lane) {
   }
 }
 
+// ---- epilogue --------------------------------------------------------------------------------------------------
+// One 32-column chunk of a thread's accumulator row: bias from SHARED memory (every lane reads the same addresses:
+// broadcast), the activation resolved ONCE per chunk (a per-element switch on a run-time value compiles to four
+// branches per element behind a dependent global bias load: ~15 SASS instructions and ~80 stall cycles per output
+// element, measured with ncu — the round-1 epilogue cost as much as the whole K loop of a 256-channel tile), then
+// 16-byte stores of the first `ncols` columns (a multiple of 8).
+template <bool F32OUT>
+__device__ __forceinline__ void epi_chunk(const uint32_t (&r)[32], const float* __restrict__ sb, int act, void* dst,
+                                          int ncols, bool valid) {
+  float f[32];
+#pragma unroll
+  for (int j = 0; j < 32; j += 4) {
+    const float4 b = *reinterpret_cast<const float4*>(sb + j);
+    f[j] = __uint_as_float(r[j]) + b.x;
+    f[j + 1] = __uint_as_float(r[j + 1]) + b.y;
+    f[j + 2] = __uint_as_float(r[j + 2]) + b.z;
+    f[j + 3] = __uint_as_float(r[j + 3]) + b.w;
+  }
+  if (act == NEMAR_ACT_LRELU) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.2f * f[j]);      // == x > 0 ? x : 0.2 x
+  } else if (act == NEMAR_ACT_RELU) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+  } else if (act == NEMAR_ACT_TANH) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) f[j] = tanhf(f[j]);
+  }
+  if (!valid) return;
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    if (g * 8 < ncols) {
+      if constexpr (F32OUT) {
+        float* o = (float*)dst + g * 8;
+        *reinterpret_cast<float4*>(o) = make_float4(f[g * 8], f[g * 8 + 1], f[g * 8 + 2], f[g * 8 + 3]);
+        *reinterpret_cast<float4*>(o + 4) = make_float4(f[g * 8 + 4], f[g * 8 + 5], f[g * 8 + 6], f[g * 8 + 7]);
+      } else {
+        uint4 pk;
+        __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&pk);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) h[j] = __floats2bfloat162_rn(f[g * 8 + 2 * j], f[g * 8 + 2 * j + 1]);
+        *reinterpret_cast<uint4*>((__nv_bfloat16*)dst + g * 8) = pk;
+      }
+    }
+  }
+}
+
+// The whole accumulator row of one tile (NCH chunks of 32 columns starting at TMEM address `taddr`): the load of chunk
+// c + 1 is in flight while chunk c is converted and stored.  `off` = element offset of the row's first column in dst;
+// `cols` = number of real columns (multiple of 8; columns beyond it are not stored).
+template <int NCH, bool F32OUT>
+__device__ __forceinline__ void epi_row(uint32_t taddr, const float* __restrict__ sbias, int act, void* dst, long long off,
+                                        int cols, bool valid) {
+  uint32_t ra[32], rb[32];
+  tmem_ld_32x32_issue(taddr, ra);
+#pragma unroll
+  for (int ch = 0; ch < NCH; ch += 2) {
+    tmem_ld_wait(ra);
+    if (ch + 1 < NCH) tmem_ld_32x32_issue(taddr + (uint32_t)(ch + 1) * 32u, rb);
+    {
+      void* d = F32OUT ? (void*)((float*)dst + off + ch * 32) : (void*)((__nv_bfloat16*)dst + off + ch * 32);
+      epi_chunk<F32OUT>(ra, sbias + ch * 32, act, d, cols - ch * 32, valid);
+    }
+    if (ch + 1 < NCH) {
+      tmem_ld_wait(rb);
+      if (ch + 2 < NCH) tmem_ld_32x32_issue(taddr + (uint32_t)(ch + 2) * 32u, ra);
+      void* d = F32OUT ? (void*)((float*)dst + off + (ch + 1) * 32) : (void*)((__nv_bfloat16*)dst + off + (ch + 1) * 32);
+      epi_chunk<F32OUT>(rb, sbias + (ch + 1) * 32, act, d, cols - (ch + 1) * 32, valid);
+    }
+  }
+}
+
+// bias of this CTA's channel tile into shared memory (zeros where there is no bias / beyond the destination channels)
+__device__ __forceinline__ void load_bias_tile(float* sbias, const float* __restrict__ bias, int c0, int cd, int bn) {
+  for (int k = threadIdx.x; k < bn; k += blockDim.x) sbias[k] = (bias && c0 + k < cd) ? __ldg(bias + c0 + k) : 0.f;
+}
+
 template <int BN, int BK>
 struct GatherCfg {
   static constexpr uint32_t A_BYTES = round1k(BM * BK * 2), B_BYTES = round1k(BN * BK * 2);
@@ -163,7 +240,7 @@ struct GatherCfg {
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : (STAGES_RAW < 2 ? 2 : STAGES_RAW);
   static constexpr uint32_t TX_BYTES = BM * BK * 2 + BN * BK * 2;
   static constexpr uint32_t ACC_COLS = BN < 32 ? 32 : BN;     // TMEM columns of one accumulator
-  static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + 1024 + 256 + (size_t)BN * 2 * sizeof(float);
+  static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + 1024 + 256 + (size_t)ACC_COLS * sizeof(float);
 };
 
 template <int BN, int BK, bool F32OUT>
@@ -178,7 +255,7 @@ tc_gather_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint64_t* empty_bar = full_bar + Cfg::STAGES;
   uint64_t* tmem_full = empty_bar + Cfg::STAGES;     // one per accumulator
   uint32_t* tmem_slot = (uint32_t*)(tmem_full + MAX_TPC);
-  float* sstat = (float*)(tmem_slot + 2);          // [BN][2] partial InstanceNorm statistics of this tile
+  float* sbias = (float*)(((uintptr_t)(tmem_slot + 2) + 15) & ~(uintptr_t)15);          // [ACC_COLS] bias of this CTA's channel tile
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // this CTA owns the consecutive destination tiles [t_first, t_first + t_count): one K pipeline runs through all
@@ -197,6 +274,7 @@ tc_gather_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     fence_mbar_init();
   }
   if (warp == 2) tmem_alloc(tmem_slot, P.tmem_cols);
+  load_bias_tile(sbias, P.bias, c0, P.cd, (int)Cfg::ACC_COLS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -254,78 +332,22 @@ tc_gather_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int q = warp & 3;
     const int row = q * 32 + lane;
     const int rx = row % P.tw, ry = (row / P.tw) % P.th, rn = row / (P.tw * P.th);
-    const int et = threadIdx.x - 64;                       // 0..127 within the epilogue warps
+    int cols = P.cd - c0;                                  // real columns of this channel tile (multiple of 8)
+    if (cols > BN) cols = BN;
 #pragma unroll 1
     for (int ti = 0; ti < t_count; ++ti) {
-    int t = t_first + ti;
-    const int tx = t % P.tiles_x; t /= P.tiles_x;
-    const int ty = t % P.tiles_y;
-    const int x0 = tx * P.tw, y0 = ty * P.th, n0 = (t / P.tiles_y) * P.tn;
-    const uint32_t acc = tmem_base + (uint32_t)ti * Cfg::ACC_COLS;
-    const int px = x0 + rx, py = y0 + ry, pn = n0 + rn;
-    const bool valid = px < P.dw && py < P.dh && pn < P.dn;
-    const long long off = (long long)pn * P.ds_n + (long long)(py * P.ostep + P.oy0) * P.ds_y +
-                          (long long)(px * P.ostep + P.ox0) * P.ds_x + c0;
-    if (P.stats) {
-      for (int k = et; k < 2 * BN; k += 128) sstat[k] = 0.f;
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-    }
-    mbar_wait(&tmem_full[ti], 0);
-    tc_fence_after();
-#pragma unroll 1
-    for (int cc = 0; cc < (int)Cfg::ACC_COLS; cc += 32) {
-      float v[32];
-      tmem_ld_32x32(acc + ((uint32_t)(q * 32) << 16) + (uint32_t)cc, v);
-      if (P.stats) {
-        // InstanceNorm statistics in the epilogue: column sums of (acc + bias) and its square over this warp's 32
-        // pixels via a transposing butterfly, combined across the four epilogue warps in shared memory
-        float s1[32], s2[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const int ch = c0 + cc + j;
-          float f = (valid && cc + j < BN && ch < P.cd) ? v[j] + (P.bias ? __ldg(P.bias + ch) : 0.f) : 0.f;
-          s1[j] = f; s2[j] = f * f;
-        }
-        warp_transpose_sum(s1, lane);
-        warp_transpose_sum(s2, lane);
-        if (cc + lane < BN) {
-          atomicAdd(&sstat[(cc + lane) * 2], s1[0]);
-          atomicAdd(&sstat[(cc + lane) * 2 + 1], s2[0]);
-        }
-      }
-      if (valid) {
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          if (cc + g * 8 < BN && c0 + cc + g * 8 < P.cd) {
-            float f[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              float b = P.bias ? __ldg(P.bias + c0 + cc + g * 8 + j) : 0.f;
-              f[j] = act_fwd(v[g * 8 + j] + b, P.act);
-            }
-            if constexpr (F32OUT) {
-              float* o = (float*)P.dst + off + cc + g * 8;
-              *reinterpret_cast<float4*>(o) = make_float4(f[0], f[1], f[2], f[3]);
-              *reinterpret_cast<float4*>(o + 4) = make_float4(f[4], f[5], f[6], f[7]);
-            } else {
-              uint4 pk;
-              __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&pk);
-#pragma unroll
-              for (int j = 0; j < 4; ++j) h[j] = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
-              *reinterpret_cast<uint4*>((__nv_bfloat16*)P.dst + off + cc + g * 8) = pk;
-            }
-          }
-        }
-      }
-    }
-    if (P.stats) {
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      // the tile lies inside one sample (host guarantees tn == 1): one global RED per (channel, statistic)
-      float* gs = P.stats + ((long long)n0 * P.cd + c0) * 2;
-      for (int k = et; k < 2 * BN; k += 128)
-        if (c0 + (k >> 1) < P.cd) atomicAdd(gs + k, sstat[k]);
-      asm volatile("bar.sync 1, 128;" ::: "memory");       // the next tile zeroes sstat again
-    }
+      int t = t_first + ti;
+      const int tx = t % P.tiles_x; t /= P.tiles_x;
+      const int ty = t % P.tiles_y;
+      const int x0 = tx * P.tw, y0 = ty * P.th, n0 = (t / P.tiles_y) * P.tn;
+      const uint32_t acc = tmem_base + (uint32_t)ti * Cfg::ACC_COLS;
+      const int px = x0 + rx, py = y0 + ry, pn = n0 + rn;
+      const bool valid = px < P.dw && py < P.dh && pn < P.dn;
+      const long long off = (long long)pn * P.ds_n + (long long)(py * P.ostep + P.oy0) * P.ds_y +
+                            (long long)(px * P.ostep + P.ox0) * P.ds_x + c0;
+      mbar_wait(&tmem_full[ti], 0);
+      tc_fence_after();
+      epi_row<(int)Cfg::ACC_COLS / 32, F32OUT>(acc + ((uint32_t)(q * 32) << 16), sbias, P.act, P.dst, off, cols, valid);
     }   // tiles of this CTA
     tc_fence_before();
   }
@@ -352,7 +374,7 @@ tc_gather_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 constexpr int PAIR_BN = 256, PAIR_BK = 64, PAIR_MAX_STAGES = 6, PAIR_MAX_TPC = 2;
 constexpr uint32_t PAIR_A_BYTES = BM * PAIR_BK * 2, PAIR_B_BYTES = (PAIR_BN / 2) * PAIR_BK * 2;
 constexpr uint32_t PAIR_STAGE_BYTES = PAIR_A_BYTES + PAIR_B_BYTES;
-static size_t pair_smem_bytes(int stages) { return (size_t)stages * PAIR_STAGE_BYTES + 1024 + 256; }
+static size_t pair_smem_bytes(int stages) { return (size_t)stages * PAIR_STAGE_BYTES + 1024 + 256 + PAIR_BN * sizeof(float); }
 
 __global__ void __launch_bounds__(NTHREADS)
 tc_gather_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -364,6 +386,7 @@ tc_gather_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   uint64_t* empty_bar = full_bar + PAIR_MAX_STAGES;
   uint64_t* tmem_full = empty_bar + PAIR_MAX_STAGES;     // one per accumulator
   uint32_t* tmem_slot = (uint32_t*)(tmem_full + PAIR_MAX_TPC);
+  float* sbias = (float*)(((uintptr_t)(tmem_slot + 2) + 15) & ~(uintptr_t)15);                // [PAIR_BN]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();               // 0 = leader (cluster = blocks 2p, 2p+1 along x)
@@ -383,6 +406,7 @@ tc_gather_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     fence_mbar_init();
   }
   if (warp == 2) tmem_alloc_pair(tmem_slot, P.tmem_cols);
+  load_bias_tile(sbias, P.bias, c0, P.cd, PAIR_BN);
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();          // the peer's barriers are initialised before anything of ours can signal them
@@ -452,27 +476,7 @@ tc_gather_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                             (long long)(px * P.ostep + P.ox0) * P.ds_x + c0;
       mbar_wait(&tmem_full[ti], 0);
       tc_fence_after();
-#pragma unroll 1
-      for (int cc = 0; cc < PAIR_BN; cc += 32) {
-        float v[32];
-        tmem_ld_32x32(acc + ((uint32_t)(q * 32) << 16) + (uint32_t)cc, v);
-        if (valid) {
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            float f[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float b = P.bias ? __ldg(P.bias + c0 + cc + g * 8 + j) : 0.f;
-              f[j] = act_fwd(v[g * 8 + j] + b, P.act);
-            }
-            uint4 pk;
-            __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&pk);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) h[j] = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
-            *reinterpret_cast<uint4*>((__nv_bfloat16*)P.dst + off + cc + g * 8) = pk;
-          }
-        }
-      }
+      epi_row<PAIR_BN / 32, false>(acc + ((uint32_t)(q * 32) << 16), sbias, P.act, P.dst, off, PAIR_BN, valid);
     }
     tc_fence_before();
   }
@@ -528,6 +532,7 @@ tc_rp3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
   uint64_t* tmem_empty = tmem_full + RP_MAX_ACCS;
   uint64_t* w_bar = tmem_empty + RP_MAX_ACCS;
   uint32_t* tmem_slot = (uint32_t*)(w_bar + 1);
+  float* sbias = (float*)(((uintptr_t)(tmem_slot + 2) + 15) & ~(uintptr_t)15);                 // [ACC_COLS]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int c0 = blockIdx.y * BN;
@@ -544,6 +549,7 @@ tc_rp3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
   uint32_t tmem_cols = 32;
   while (tmem_cols < (uint32_t)NA * ACC_COLS) tmem_cols <<= 1;
   if (warp == 2) tmem_alloc(tmem_slot, tmem_cols);
+  load_bias_tile(sbias, P.bias, c0, P.cd, (int)ACC_COLS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -611,6 +617,8 @@ tc_rp3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
     const int q = warp & 3;
     const int row = q * 32 + lane;
     const int rx = row % RP_TW, ry = row / RP_TW;
+    int cols = P.cd - c0;
+    if (cols > BN) cols = BN;
     int i = 0;
     for (int tile = blockIdx.x; tile < R.tiles_total; tile += gridDim.x, ++i) {
       const int a = i % NA;
@@ -624,42 +632,12 @@ tc_rp3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
       const uint32_t acc = tmem_base + (uint32_t)a * ACC_COLS;
       mbar_wait(&tmem_full[a], aphase);
       tc_fence_after();
-      float v[ACC_COLS];
-#pragma unroll
-      for (int cc = 0; cc < (int)ACC_COLS; cc += 32) {
-        float w[32];
-        tmem_ld_32x32(acc + ((uint32_t)(q * 32) << 16) + (uint32_t)cc, w);
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[cc + j] = w[j];
-      }
-      // the values are in registers: hand the accumulator back before the stores
+      // (the accumulator is handed back only after the row has been stored: with <= 64 columns the row is one or
+      //  two chunk loads, and there are RP_MAX_ACCS accumulators in flight)
+      epi_row<(int)ACC_COLS / 32, F32OUT>(acc + ((uint32_t)(q * 32) << 16), sbias, P.act, P.dst, off, cols, valid);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[a]);
-      if (valid) {
-#pragma unroll
-        for (int g = 0; g < (int)ACC_COLS / 8; ++g) {
-          if (g * 8 < BN && c0 + g * 8 < P.cd) {
-            float f[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float b = P.bias ? __ldg(P.bias + c0 + g * 8 + j) : 0.f;
-              f[j] = act_fwd(v[g * 8 + j] + b, P.act);
-            }
-            if constexpr (F32OUT) {
-              float* o = (float*)P.dst + off + g * 8;
-              *reinterpret_cast<float4*>(o) = make_float4(f[0], f[1], f[2], f[3]);
-              *reinterpret_cast<float4*>(o + 4) = make_float4(f[4], f[5], f[6], f[7]);
-            } else {
-              uint4 pk;
-              __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&pk);
-#pragma unroll
-              for (int j = 0; j < 4; ++j) h[j] = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
-              *reinterpret_cast<uint4*>((__nv_bfloat16*)P.dst + off + g * 8) = pk;
-            }
-          }
-        }
-      }
     }
     tc_fence_before();
   }
@@ -859,7 +837,7 @@ static bool plan_rp3(const GatherParams& P, int taps_total, int BN, int BK, Rp3P
   R.taps_total = taps_total;
   const size_t w_total = (size_t)taps_total * P.kchunks * R.wtile_bytes;
   const size_t stage = (size_t)P.kchunks * R.patch_bytes;
-  const size_t fixed = 1024 /*alignment*/ + 512 /*barriers*/ + w_total;
+  const size_t fixed = 1024 /*alignment*/ + 1024 /*barriers + bias tile*/ + w_total;
   if (fixed + 2 * stage > 232448) return false;
   static const int st_env = [] { const char* e = getenv("NEMAR_TC_RP3_STAGES"); return e ? atoi(e) : 6; }();
   int stages = (int)((232448 - fixed) / stage);
@@ -925,7 +903,6 @@ int tc_gather_gemm(const nemar_tensor* src_in, const nemar_tensor* dst_in, const
   if (rc) return rc;
 
   const int nclass = (gg.sd == 2) ? 4 : 1;
-  bool fused_stats = stats != nullptr;
   if (stats) NEMAR_REQUIRE(act == NEMAR_ACT_NONE, "tc_gather_gemm: statistics need the pre-activation output");
   for (int cls = 0; cls < nclass; ++cls) {
     GatherParams P;
@@ -952,8 +929,7 @@ int tc_gather_gemm(const nemar_tensor* src_in, const nemar_tensor* dst_in, const
     NEMAR_REQUIRE(P.ntaps > 0, "tc_gather_gemm: parity class without taps");
     P.kchunks = src.c / BK;
     P.cs = src.c;
-    static const int fuse_env = [] { const char* e = getenv("NEMAR_FUSED_STATS"); return e ? atoi(e) : 0; }();
-    pick_tile(P.dw, P.dh, P.dn, P.tw, P.th, P.tn, BM, fuse_env && stats);
+    pick_tile(P.dw, P.dh, P.dn, P.tw, P.th, P.tn, BM);
     P.tiles_x = (P.dw + P.tw - 1) / P.tw;
     P.tiles_y = (P.dh + P.th - 1) / P.th;
     P.tiles_n = (P.dn + P.tn - 1) / P.tn;
@@ -965,15 +941,9 @@ int tc_gather_gemm(const nemar_tensor* src_in, const nemar_tensor* dst_in, const
     P.act = act;
     static const int stag = [] { const char* e = getenv("NEMAR_TC_STAGGER"); return e ? atoi(e) : 0; }();   // measured: no effect on B200 (not an L2 hot-spot problem)
     P.kstagger = stag;
-    // statistics are fused when every tile lies inside one sample; tiny maps (several samples per tile) use the
-    // separate reduction pass below
-    static const int fuse = [] { const char* e = getenv("NEMAR_FUSED_STATS"); return e ? atoi(e) : 0; }();
-    // (measured on B200: the butterfly + REDs lengthen the epilogue by more than the separate L2-resident
-    //  reduction pass costs, so the fused variant is opt-in: NEMAR_FUSED_STATS=1)
-    P.stats = (fuse && stats && P.tn == 1 && !f32) ? stats : nullptr;
-    if (stats && !P.stats) fused_stats = false;
+    P.stats = nullptr;
     static const int rp3_env = [] { const char* e = getenv("NEMAR_TC_RP3"); return e ? atoi(e) : 0; }();
-    if (rp3_env && !pair && gg.sm == 1 && gg.sd == 1 && !P.stats) {
+    if (rp3_env && !pair && gg.sm == 1 && gg.sd == 1) {
       Rp3Params R;
       size_t rp_smem = 0;
       if (plan_rp3(P, taps_total, BN, BK, R, rp_smem)) {
@@ -1008,8 +978,8 @@ int tc_gather_gemm(const nemar_tensor* src_in, const nemar_tensor* dst_in, const
     }
     if (rc) return rc;
   }
-  if (stats && !fused_stats) {
-    // (mixed fused / unfused classes cannot occur: tn depends only on the class extents, which differ by <= 1)
+  if (stats) {
+    // InstanceNorm statistics of the (L2-resident) output: separate reduction pass
     cudaMemsetAsync(stats, 0, sizeof(float) * 2 * (size_t)dst.n * dst.c, s);
     return nemar_instnorm_stats(dst_in, stats, (void*)s);
   }

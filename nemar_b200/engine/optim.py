@@ -58,9 +58,12 @@ class FlatAdam:
 
     def state_dict(self):
         return {"step": self.step_count, "exp_avg": self.exp_avg.detach().cpu().clone(),
-                "exp_avg_sq": self.exp_avg_sq.detach().cpu().clone(), "lr": self.param_groups[0]["lr"]}
+                "exp_avg_sq": self.exp_avg_sq.detach().cpu().clone(), "lr": self.param_groups[0]["lr"],
+                "layout": [int(p.numel()) for p in self.params]}
 
     def load_state_dict(self, sd):
+        if "layout" in sd and list(sd["layout"]) != [int(p.numel()) for p in self.params]:
+            raise ValueError("optimizer state was saved for another parameter layout")
         self.step_count = int(sd["step"])
         self.step_dev.fill_(self.step_count)
         self.exp_avg.copy_(sd["exp_avg"])

@@ -97,9 +97,43 @@ class NEMARModel(BaseModel):
         # replicas must start identical whatever each process's RNG did before this point
         parallel.broadcast_buffers([self.optimizer_TR.flat_p, self.optimizer_D.flat_p])
 
+    # -- checkpoints: the reference's three files, plus what it forgets -------------------------------------------
+    def save_networks(self, epoch):
+        """<epoch>_net_{T,R,D}.pth exactly as the reference writes them (base_model.py:148-164), plus two files a
+        reference loader never looks for: the extra discriminators of --multi_resolution (plain list in the reference,
+        nemar_model.py:108-113, hence never saved there) and the state of both Adam optimizers."""
+        BaseModel.save_networks(self, epoch)
+        if not self.isTrain:
+            return
+        import collections
+        for i, net in enumerate(self.netD_multiresolution):
+            sd = collections.OrderedDict((k, v.detach().cpu().clone()) for k, v in net.state_dict().items())
+            torch.save(sd, os.path.join(self.save_dir, "%s_net_D_ms%d.pth" % (epoch, i + 1)))
+        torch.save({"TR": self.optimizer_TR.state_dict(), "D": self.optimizer_D.state_dict()},
+                   os.path.join(self.save_dir, "%s_optim.pth" % epoch))
+
+    def load_networks(self, epoch):
+        BaseModel.load_networks(self, epoch)
+        if not self.isTrain:
+            return
+        for i, net in enumerate(self.netD_multiresolution):
+            path = os.path.join(self.save_dir, "%s_net_D_ms%d.pth" % (epoch, i + 1))
+            if os.path.exists(path):          # absent in checkpoints written by the reference
+                net.load_state_dict(torch.load(path, map_location="cpu"))
+        path = os.path.join(self.save_dir, "%s_optim.pth" % epoch)
+        if os.path.exists(path):
+            sd = torch.load(path, map_location="cpu")
+            self.optimizer_TR.load_state_dict(sd["TR"])
+            self.optimizer_D.load_state_dict(sd["D"])
+        F.bump_weights_epoch()
+        parallel.broadcast_buffers([self.optimizer_TR.flat_p, self.optimizer_D.flat_p])
+
     def set_input(self, input):
         AtoB = self.opt.direction == "AtoB"
         a, b = ("A", "B") if AtoB else ("B", "A")
+        ready = input.get("_ready") if isinstance(input, dict) else None
+        if ready is not None:            # staged by data.prefetch.DevicePrefetcher on a side stream
+            torch.cuda.current_stream().wait_event(ready)
         if getattr(self, "_graph_inputs", None) is not None and input[a].shape == self._graph_inputs[0].shape:
             # graph mode: the captured kernels read these two static buffers
             self._graph_inputs[0].copy_(input[a], non_blocking=True)

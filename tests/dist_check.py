@@ -89,8 +89,9 @@ def main():
     # 3. same step, N ranks vs one process
     g_dp = step_and_capture(dp, a, b)
     calls = dp.allreduce.calls
+    # (every rank constructs the reference model: construction broadcasts parameters, a collective; only rank 0 steps it)
+    single = build(per * world, 7)
     if rank == 0:
-        single = build(per * world, 7)
         single.optimizer_TR.grad_hook = lambda flat: 1.0       # no exchange: the whole global batch is local
         single.optimizer_D.grad_hook = lambda flat: 1.0
         single.optimizer_TR.flat_p.copy_(p0["TR"])

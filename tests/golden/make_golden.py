@@ -39,6 +39,10 @@ CASES = {
                        alpha=1.0, multires_reg=3, multi_resolution=3, ngf=16, ndf=16,
                        extra=["--netG", "resnet_9blocks", "--lambda_smooth", "200.0", "--stn_bilateral_alpha", "1.0",
                               "--stn_multires_reg", "3", "--multi_resolution", "3", "--ngf", "16", "--ndf", "16"]),
+    # C5 shape: 1024x1024 dense deformation field, resnet_9blocks, batch 1 (reduced widths keep the CPU replay short)
+    "c5_1024": dict(stn_type="unet", n_blocks=9, height=1024, width=1024, batch=1, steps=1, lambda_smooth=200.0,
+                    ngf=8, ndf=8,
+                    extra=["--netG", "resnet_9blocks", "--lambda_smooth", "200.0", "--ngf", "8", "--ndf", "8"]),
     # ragged edge case: non-square, not a multiple of 128 (the seven floor-pools of the ResUnet go 288 -> 2 and
     # 384 -> 3 through odd extents 9 and 3; the up path resizes to each skip's size), batch 2
     "ragged288x384": dict(stn_type="unet", n_blocks=6, height=288, width=384, batch=2, steps=2, lambda_smooth=200.0,

@@ -15,6 +15,8 @@ CASE_FLAGS = {
                         multires_reg=3, multi_resolution=3, ngf=16, ndf=16), 1,
                    ["--netG", "resnet_9blocks", "--lambda_smooth", "200.0", "--stn_bilateral_alpha", "1.0",
                     "--stn_multires_reg", "3", "--multi_resolution", "3", "--ngf", "16", "--ndf", "16"]),
+    "c5_1024": (dict(stn_type="unet", n_blocks=9, height=1024, width=1024, lambda_smooth=200.0, ngf=8, ndf=8), 1,
+                ["--netG", "resnet_9blocks", "--lambda_smooth", "200.0", "--ngf", "8", "--ndf", "8"]),
     "ragged288x384": (dict(stn_type="unet", n_blocks=6, height=288, width=384, lambda_smooth=200.0, ngf=16, ndf=16), 2,
                       ["--netG", "resnet_6blocks", "--lambda_smooth", "200.0", "--ngf", "16", "--ndf", "16"]),
 }

@@ -202,3 +202,24 @@ def test_cuda_graph_mode_state_machine(monkeypatch):
         m2.set_input(batch(k))
         m2._optimize_parameters_graphed()
     assert len(ran) == 6 and len(FakeGraph.made) == 2
+
+
+def test_reference_written_checkpoint_loads():
+    """tests/golden/refckpt/*.pth were written by the REFERENCE's own BaseModel.save_networks
+    (tests/golden/make_ref_checkpoint.py); the engine's modules must take them key for key, value for value."""
+    from nemar_b200.models import networks
+    d = os.path.join(ROOT, "tests", "golden", "refckpt")
+    netT = networks.define_G(3, 3, 8, "resnet_6blocks", "instance", False, "normal", 0.02, ())
+    netD = networks.define_D(6, 8, "basic", 3, "instance", "normal", 0.02, ())
+    for net, name in ((netT, "T"), (netD, "D")):
+        sd = torch.load(os.path.join(d, "latest_net_%s.pth" % name), map_location="cpu")
+        assert list(sd.keys()) == list(net.state_dict().keys())
+        net.load_state_dict(sd)
+        assert all(torch.equal(v, sd[k]) for k, v in net.state_dict().items())
+
+
+def test_device_prefetcher_passthrough_on_cpu():
+    from nemar_b200.data.prefetch import DevicePrefetcher
+    batches = [{"A": torch.full((2, 3, 4, 4), float(i)), "B": torch.zeros(2, 3, 4, 4), "A_paths": "a%d" % i} for i in range(3)]
+    got = list(DevicePrefetcher(batches, "cpu"))
+    assert [float(b["A"][0, 0, 0, 0]) for b in got] == [0.0, 1.0, 2.0] and got[1]["A_paths"] == "a1" and len(DevicePrefetcher(batches, "cpu")) == 3

@@ -61,7 +61,8 @@ BOUNDS = {"fp32": (2e-3, 2e-3, 2e-3), "bf16": (0.15, 0.15, 0.15)}
 @pytest.mark.parametrize("precision,engine", [("fp32", "generic"), ("bf16", "generic"), ("bf16", "auto")])
 def test_gradients_at_trained_state_vs_fp64_oracle(precision, engine):
     cfg, T, R, Ds, A, B = _trained_state()
-    model, _, _, _ = H.build_case("c1_affine64", precision=precision, conv_engine=engine, more_flags=["--lr", "0"])
+    # default lr on both sides: the T/R phase differentiates through the discriminator AFTER its Adam update
+    model, _, _, _ = H.build_case("c1_affine64", precision=precision, conv_engine=engine)
     H.load_states(model, T, R, Ds)
     H.run_engine_steps(model, A, B, 1)
     truth = _oracle_grads(cfg, T, R, Ds, A, B, torch.float64)

@@ -59,9 +59,9 @@ def _grids(n, h, w, seed):
                 wild=torch.rand((n, h, w, 2), generator=g) * 2.2 - 1.1)
 
 
-@pytest.mark.parametrize("h,w", [(64, 64), (37, 53), (256, 256), (30, 2)])
+@pytest.mark.parametrize("h,w", [(64, 64), (37, 53), (256, 256), (30, 2), (512, 512), (1024, 1024), (288, 384)])
 def test_grid_sample_indices_bit_exact_and_values(h, w):
-    n, c = 2, 3
+    n, c = (1 if h * w >= 512 * 512 else 2), 3
     img = gen(n, c, h, w, seed=3)
     for name, grid in _grids(n, h, w, 5).items():
         out, idx = F.grid_sample_indices(grid.to(DEV), img.to(DEV))

@@ -17,6 +17,7 @@ CASES = {
                                     multires_reg=2, multi_resolution=2, ngf=16, ndf=16), batch=1),
     "c4_ms3_512": dict(cfg=dict(stn_type="unet", n_blocks=9, height=512, width=512, lambda_smooth=200.0, alpha=1.0,
                                 multires_reg=3, multi_resolution=3, ngf=16, ndf=16), batch=1),
+    "c5_1024": dict(cfg=dict(stn_type="unet", n_blocks=9, height=1024, width=1024, lambda_smooth=200.0, ngf=8, ndf=8), batch=1),
     "ragged288x384": dict(cfg=dict(stn_type="unet", n_blocks=6, height=288, width=384, lambda_smooth=200.0, ngf=16, ndf=16),
                           batch=2),
 }
@@ -36,7 +37,7 @@ def run_oracle(name, steps):
     return st, np.array(losses), first
 
 
-@pytest.mark.parametrize("name", ["c1_affine64", "c4_multires256", "c2_unet256", "c4_ms3_512", "ragged288x384"])
+@pytest.mark.parametrize("name", ["c1_affine64", "c4_multires256", "c2_unet256", "c4_ms3_512", "ragged288x384", "c5_1024"])
 def test_oracle_matches_reference_golden(name):
     g = np.load(os.path.join(GOLD, name + ".npz"))
     steps = 1 if name == "c2_unet256" else g["losses"].shape[0]   # the 256^2 resnet_9 case is slow on CPU

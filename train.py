@@ -29,9 +29,24 @@ def _maybe_spawn():
     sys.exit(subprocess.call(cmd))
 
 
+class _Mapped:
+    """iterable view of a loader with a function applied to every batch"""
+
+    def __init__(self, loader, fn):
+        self.loader, self.fn = loader, fn
+
+    def __len__(self):
+        return len(self.loader)
+
+    def __iter__(self):
+        for d in self.loader:
+            yield self.fn(d)
+
+
 def main():
     _maybe_spawn()
     from nemar_b200.data import create_dataset
+    from nemar_b200.data.prefetch import DevicePrefetcher
     from nemar_b200.engine import parallel
     from nemar_b200.models import create_model
     from nemar_b200.options.train_options import TrainOptions
@@ -47,19 +62,21 @@ def main():
     model.setup(opt)
     visualizer = Visualizer(opt)
     total_iters = 0
+    # device input pipeline: each rank stages ITS shard of the next global batch (pinned, side stream) while it computes
+    shard = (lambda d: {k: (parallel.shard_batch(v, rank, world) if torch.is_tensor(v) else v) for k, v in d.items()}) \
+        if world > 1 else (lambda d: d)
+    batches = DevicePrefetcher(_Mapped(dataset, shard), model.device) if opt.gpu_ids else _Mapped(dataset, shard)
     for epoch in range(opt.epoch_count, opt.niter + opt.niter_decay + 1):
         epoch_start_time = time.time()
         iter_data_time = time.time()
         epoch_iter = 0
-        for i, data in enumerate(dataset):
+        for i, data in enumerate(batches):
             iter_start_time = time.time()
             if total_iters % opt.print_freq == 0:
                 t_data = iter_start_time - iter_data_time
             visualizer.reset()
             total_iters += opt.batch_size
             epoch_iter += opt.batch_size
-            if world > 1:   # every rank sees the same global batch and keeps its shard
-                data = {k: (parallel.shard_batch(v, rank, world) if torch.is_tensor(v) else v) for k, v in data.items()}
             model.set_input(data)
             model.optimize_parameters()
             if total_iters % opt.display_freq == 0:
