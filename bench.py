@@ -144,13 +144,16 @@ def run_engine(args):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for data in feed:
+        host_loss = torch.zeros(steps, dtype=torch.float32).pin_memory() if read_loss else None
+        for i, data in enumerate(feed):
             model.set_input(data)
             model.optimize_parameters()
-            if read_loss:
-                _ = float(model.loss_D.detach())        # device -> host read of the step's result
+            if read_loss:       # device -> host read of every step's result: async D2H into pinned memory, consumed after the loop
+                host_loss[i:i + 1].copy_(model.loss_D.detach().reshape(1), non_blocking=True)
         e1.record()
         barrier()
+        if read_loss:
+            assert bool(torch.isfinite(host_loss).all()), "a step's loss did not reach the host"
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
@@ -360,6 +363,8 @@ def torch_gpu_reference(args, dev, steps=5):
     res = {}
     A, B = O.synthetic_batch(args.batch, args.size, args.size, seed=1)
     A, B = A.to(dev), B.to(dev)
+    old_default = torch.get_default_device() if hasattr(torch, "get_default_device") else None
+    torch.set_default_device(dev)      # the oracle builds its identity grids / targets with the default device
     for name, tf32 in (("fp32", False), ("tf32", True)):
         torch.backends.cudnn.allow_tf32 = tf32
         torch.backends.cuda.matmul.allow_tf32 = tf32
@@ -379,6 +384,7 @@ def torch_gpu_reference(args, dev, steps=5):
         del st
         torch.cuda.empty_cache()
     torch.backends.cudnn.allow_tf32 = True
+    torch.set_default_device(old_default if old_default is not None else "cpu")
     res["kind"] = "port"
     res["what"] = ("the reference's optimize_parameters restated in torch (oracle/nemar_oracle.py, golden-pinned to the reference) "
                    "run eagerly on cuda:0, batch %d: ATen/cuDNN kernels, fp32 storage; 'tf32' = same with TF32 tensor-core math "

@@ -101,6 +101,19 @@ int nemar_copy_view_bwd(const nemar_tensor* dsrc_out, const nemar_tensor* ddst_i
 int nemar_pack_weights(const float* w /* reference layout */, const nemar_conv_geom* g, int dtype,
                        int cin_p, int cout_p, void* wf /* may be NULL */, void* wd /* may be NULL */,
                        void* stream);
+/* Every pack of an optimizer's layers in ONE launch (the per-layer call above costs 152 launches per training step at
+ * C2).  jobs_dev: device array of nemar_pack_job — the element mapping of ONE pack of nemar_pack_weights
+ * (out[o][kh][kw][i] chunk-major, zero padded; w indexed [o][i] or [i][o]; taps optionally flipped), or with kind == 2 a
+ * zero-padded fp32 vector copy (padded bias).  blocks_dev: nblocks pairs (job index, 2048-element slice index). */
+typedef struct nemar_pack_job {
+  const float* w;
+  void* out;
+  int32_t O, op, I, ip, kh, kw, w_is_oi, flip;
+  int32_t dtype; /* NEMAR_F32 / NEMAR_BF16 of `out` */
+  int32_t kind;  /* 1: weight pack, 2: padded vector copy */
+} nemar_pack_job;
+int nemar_pack_weights_multi(const nemar_pack_job* jobs_dev, const int* blocks_dev, int nblocks, void* stream);
+
 /* y = act(conv(x) + bias); x halo (if any) is consumed as real data ("valid" conv over the padded
  * buffer when x->pad == g->pad with reflect halo; zero padding needs no halo).  If stats != NULL,
  * per-(n,cout) [sum, sum of squares] of the pre-activation fp32 values are accumulated into
@@ -136,11 +149,13 @@ int nemar_norm_act_fwd(const nemar_tensor* x, const float* stats /* NULL: no nor
 int nemar_norm_act_bwd_reduce(const nemar_tensor* x, const float* stats, int act,
                               const nemar_tensor* dy, int pad_mode, float* red, void* stream);
 /* phase B: dx = rstd*(g - mean(g) - xhat*mean(g*xhat)) (or g when stats==NULL);
- *          dres (optional) (=|+=) fold(dy);  db (optional, [c] floats, overwritten) = sum over n,h,w of dx —
- *          the bias gradient of the convolution that produced x, fused into this pass */
+ *          dres (optional) (=|+=) fold(dy);  db (optional, [c] floats) (=|+=) sum over n,h,w of dx — the bias gradient
+ *          of the convolution that produced x, fused into this pass.
+ *          flags: bit 0 = dres accumulates, bit 1 = db accumulates (e.g. straight into the optimizer's gradient
+ *          bucket), bit 2 = zero the halo ring of dres here (the pass writes only its interior) */
 int nemar_norm_act_bwd_apply(const nemar_tensor* x, const float* stats, int act,
                              const nemar_tensor* dy, int pad_mode, const float* red,
-                             const nemar_tensor* dx, const nemar_tensor* dres, int dres_accumulate,
+                             const nemar_tensor* dx, const nemar_tensor* dres, int flags,
                              float* db, void* stream);
 /* dx = dy * act'(y) for an activation fused in a conv epilogue (uses the OUTPUT y) */
 int nemar_act_bwd(const nemar_tensor* y, const nemar_tensor* dy, int act, const nemar_tensor* dx,
@@ -232,6 +247,13 @@ int nemar_adam_step_dev(float* p, const float* g, float* m, float* v, int64_t nu
 /* Dropout(0.5) of the ResnetBlock (networks.py:427-428): counter-based mask, y = keep ? 2x : 0 */
 int nemar_dropout(const nemar_tensor* x, const nemar_tensor* y, uint64_t seed, uint64_t offset,
                   void* stream);
+
+/* Same mask generator, keyed by (seed, salt, *step_dev): the step number is read from DEVICE memory so that a step
+ * captured in a CUDA graph draws a new mask on every replay (forward and backward of one step read the same value).
+ * nemar_counter_add bumps such a counter in stream order. */
+int nemar_dropout_dev(const nemar_tensor* x, const nemar_tensor* y, uint64_t seed, uint64_t salt,
+                      const int64_t* step_dev, void* stream);
+int nemar_counter_add(int64_t* counter_dev, int64_t v, void* stream);
 
 #ifdef __cplusplus
 }

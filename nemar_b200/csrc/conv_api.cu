@@ -32,6 +32,11 @@ NEMAR_API int nemar_pack_weights(const float* w, const nemar_conv_geom* g, int d
   return rc;
 }
 
+NEMAR_API int nemar_pack_weights_multi(const nemar_pack_job* jobs_dev, const int* blocks_dev, int nblocks, void* stream) {
+  NEMAR_REQUIRE(jobs_dev && blocks_dev && nblocks > 0, "pack_weights_multi: bad args");
+  return generic_pack_multi(jobs_dev, blocks_dev, nblocks, (cudaStream_t)stream);
+}
+
 static int expected_out(int in, const nemar_conv_geom* g) {
   return (in + 2 * g->pad - g->kh) / g->stride + 1;
 }

@@ -223,7 +223,44 @@ __global__ void pack_kernel(const float* __restrict__ w, T* __restrict__ out, in
   }
 }
 
+// ---- multi-tensor packing: every layer of an optimizer in ONE launch --------------------------------------------
+// jobs[j] describes one pack (or, with kind 2, one zero-padded fp32 bias copy); blocks[b] = (job, first element of the
+// 2048-element slice this block handles).  Same element mapping as pack_kernel.
+__global__ void __launch_bounds__(256) pack_multi_kernel(const nemar_pack_job* __restrict__ jobs, const int2* __restrict__ blocks) {
+  const int2 bj = blocks[blockIdx.x];
+  const nemar_pack_job J = jobs[bj.x];
+  const int64_t total = (int64_t)J.op * J.kh * J.kw * J.ip;
+  const int64_t lo = (int64_t)bj.y * 2048;
+  const int bk = (J.kind == 2) ? 0 : packed_bk(J.ip);
+#pragma unroll
+  for (int u = 0; u < 8; ++u) {
+    const int64_t idx = lo + u * 256 + threadIdx.x;
+    if (idx >= total) break;
+    int i = (int)(idx % J.ip);
+    int64_t r = idx / J.ip;
+    int b = (int)(r % J.kw); r /= J.kw;
+    int a = (int)(r % J.kh);
+    int o = (int)(r / J.kh);
+    float v = 0.f;
+    if (i < J.I && o < J.O) {
+      int aa = J.flip ? J.kh - 1 - a : a, bb = J.flip ? J.kw - 1 - b : b;
+      int64_t widx = J.w_is_oi ? (((int64_t)o * J.I + i) * J.kh + aa) * J.kw + bb
+                               : (((int64_t)i * J.O + o) * J.kh + aa) * J.kw + bb;
+      v = __ldg(J.w + widx);
+    }
+    const int64_t oidx = bk ? packed_index(o, a * J.kw + b, i, J.op, J.ip, bk) : idx;
+    if (J.dtype == NEMAR_BF16) ((__nv_bfloat16*)J.out)[oidx] = __float2bfloat16(v);
+    else ((float*)J.out)[oidx] = v;
+  }
+}
+
 }  // namespace
+
+int generic_pack_multi(const nemar_pack_job* jobs_dev, const int* blocks_dev, int nblocks, cudaStream_t s) {
+  pack_multi_kernel<<<nblocks, 256, 0, s>>>(jobs_dev, (const int2*)blocks_dev);
+  NEMAR_LAUNCH_CHECK();
+  return 0;
+}
 
 int generic_gather_gemm(const nemar_tensor* src, const nemar_tensor* dst, const void* wp, int w_dtype, int wp_cs,
                         const float* bias, int act, const GatherGeom& gg, cudaStream_t s) {

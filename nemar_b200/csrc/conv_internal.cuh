@@ -25,6 +25,8 @@ struct GatherGeom {
   int dst_padded;  // 1: iterate over the destination's padded index space (gradient into a halo'd buffer)
 };
 
+int generic_pack_multi(const nemar_pack_job* jobs_dev, const int* blocks_dev, int nblocks, cudaStream_t s);
+
 // generic (CUDA-core) engine — conv_generic.cu
 int generic_gather_gemm(const nemar_tensor* src, const nemar_tensor* dst, const void* wp, int w_dtype, int wp_cs,
                         const float* bias, int act, const GatherGeom& gg, cudaStream_t s);

@@ -280,41 +280,46 @@ tc_gather_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  // Producer and MMA warps stay CONVERGED and elect one lane per issue (elect.sync): inside a plain `lane == 0` branch
+  // ptxas cannot treat the TMA / tcgen05 operands as warp-uniform and wraps every UTMALDG / UTCHMMA / UTCBAR in a
+  // "waterfall" loop (ELECT, R2UR.BROADCAST, BRA.U.ANY) — measured 219 clk per MMA whatever its N, i.e. the tensor pipe
+  // capped at 29 % per CTA for N = 128 (scripts/probe/umma_rate_probe.cu, profiles/r02_umma_rate_probe.txt).
   if (warp == 0) {
-    if (lane == 0) {
-      // ===== TMA producer =====
-      int stage = 0; uint32_t phase = 0;
-      // every CTA walks the K loop from a different starting step (the accumulation order is irrelevant): CTAs
-      // running concurrently then fetch DIFFERENT weight tiles instead of hammering the same L2 lines
-      int kk = P.kstagger ? (int)((blockIdx.x * 5u + blockIdx.y * 3u) % (unsigned)ksteps) : 0;
-      for (int ti = 0; ti < t_count; ++ti) {
-        int t = t_first + ti;
-        const int tx = t % P.tiles_x; t /= P.tiles_x;
-        const int ty = t % P.tiles_y;
-        const int x0 = tx * P.tw, y0 = ty * P.th, n0 = (t / P.tiles_y) * P.tn;
-        for (int ks = 0; ks < ksteps; ++ks) {
-          const int tap = kk / P.kchunks, kc = kk - tap * P.kchunks;
-          if (++kk == ksteps) kk = 0;
-          mbar_wait(&empty_bar[stage], phase ^ 1);
+    // ===== TMA producer =====
+    int stage = 0; uint32_t phase = 0;
+    // every CTA walks the K loop from a different starting step (the accumulation order is irrelevant): CTAs
+    // running concurrently then fetch DIFFERENT weight tiles instead of hammering the same L2 lines
+    int kk = P.kstagger ? (int)((blockIdx.x * 5u + blockIdx.y * 3u) % (unsigned)ksteps) : 0;
+    for (int ti = 0; ti < t_count; ++ti) {
+      int t = t_first + ti;
+      const int tx = t % P.tiles_x; t /= P.tiles_x;
+      const int ty = t % P.tiles_y;
+      const int x0 = tx * P.tw, y0 = ty * P.th, n0 = (t / P.tiles_y) * P.tn;
+      for (int ks = 0; ks < ksteps; ++ks) {
+        const int tap = kk / P.kchunks, kc = kk - tap * P.kchunks;
+        if (++kk == ksteps) kk = 0;
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        if (elect_one()) {
           uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
           mbar_expect_tx(&full_bar[stage], Cfg::TX_BYTES);
           tma_load_4d(sa, &tmA, &full_bar[stage], kc * BK, x0 * P.sm + P.tdx[tap], y0 * P.sm + P.tdy[tap], n0);
           tma_load_3d(sa + Cfg::A_BYTES, &tmB, &full_bar[stage], 0, c0, P.twi[tap] * P.kchunks + kc);
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ===== MMA issuer =====
-      constexpr uint32_t idesc = make_idesc_bf16(BM, BN, 0, 0);
-      constexpr uint32_t SBO = 8 * BK * 2;     // 8 rows of one swizzle atom
-      int stage = 0; uint32_t phase = 0;
-      for (int ti = 0; ti < t_count; ++ti) {
-        const uint32_t acc = tmem_base + (uint32_t)ti * Cfg::ACC_COLS;
-        for (int ks = 0; ks < ksteps; ++ks) {
-          mbar_wait(&full_bar[stage], phase);
-          tc_fence_after();
+    // ===== MMA issuer =====
+    constexpr uint32_t idesc = make_idesc_bf16(BM, BN, 0, 0);
+    constexpr uint32_t SBO = 8 * BK * 2;     // 8 rows of one swizzle atom
+    int stage = 0; uint32_t phase = 0;
+    for (int ti = 0; ti < t_count; ++ti) {
+      const uint32_t acc = tmem_base + (uint32_t)ti * Cfg::ACC_COLS;
+      for (int ks = 0; ks < ksteps; ++ks) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        if (elect_one()) {
           const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
           const uint64_t adesc = make_smem_desc(sa, 16, SBO, layout_for(BK));
           const uint64_t bdesc = make_smem_desc(sa + Cfg::A_BYTES, 16, SBO, layout_for(BK));
@@ -322,9 +327,10 @@ tc_gather_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           for (int k = 0; k < BK / 16; ++k)   // +32 bytes per UMMA_K inside the swizzled row
             umma_bf16(acc, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (ks > 0 || k > 0) ? 1u : 0u);
           umma_commit(&empty_bar[stage]);
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          if (ks == ksteps - 1) umma_commit(&tmem_full[ti]);
         }
-        umma_commit(&tmem_full[ti]);
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
   } else {
@@ -414,29 +420,30 @@ tc_gather_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
-      // ===== TMA producer (both CTAs) =====
-      const uint32_t full_leader = mapa_u32(smem_u32(&full_bar[0]), 0);
-      int stage = 0; uint32_t phase = 0;
-      for (int ti = 0; ti < p_count; ++ti) {
-        int t = (p_first + ti) * 2 + (int)rank;      // t == tiles_total (odd count): every row out of bounds -> zeros
-        const int tx = t % P.tiles_x; t /= P.tiles_x;
-        const int ty = t % P.tiles_y;
-        const int x0 = tx * P.tw, y0 = ty * P.th, n0 = (t / P.tiles_y) * P.tn;
-        for (int ks = 0; ks < ksteps; ++ks) {
-          const int tap = ks / P.kchunks, kc = ks - tap * P.kchunks;
-          mbar_wait(&empty_bar[stage], phase ^ 1);
+    // ===== TMA producer (both CTAs); converged warp, one elected lane issues (see tc_gather_kernel) =====
+    const uint32_t full_leader = mapa_u32(smem_u32(&full_bar[0]), 0);
+    int stage = 0; uint32_t phase = 0;
+    for (int ti = 0; ti < p_count; ++ti) {
+      int t = (p_first + ti) * 2 + (int)rank;      // t == tiles_total (odd count): every row out of bounds -> zeros
+      const int tx = t % P.tiles_x; t /= P.tiles_x;
+      const int ty = t % P.tiles_y;
+      const int x0 = tx * P.tw, y0 = ty * P.th, n0 = (t / P.tiles_y) * P.tn;
+      for (int ks = 0; ks < ksteps; ++ks) {
+        const int tap = ks / P.kchunks, kc = ks - tap * P.kchunks;
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        if (elect_one()) {
           uint8_t* sa = smem + stage * PAIR_STAGE_BYTES;
           if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * PAIR_STAGE_BYTES);
           const uint32_t fb = full_leader + (uint32_t)stage * 8u;
           tma_load_4d_pair(sa, &tmA, fb, kc * PAIR_BK, x0 * P.sm + P.tdx[tap], y0 * P.sm + P.tdy[tap], n0);
           tma_load_3d_pair(sa + PAIR_A_BYTES, &tmB, fb, 0, c0 + (int)rank * (PAIR_BN / 2), P.twi[tap] * P.kchunks + kc);
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0 && rank == 0) {
+    if (rank == 0) {
       // ===== MMA issuer (leader CTA only) =====
       constexpr uint32_t idesc = make_idesc_bf16(2 * BM, PAIR_BN, 0, 0);
       constexpr uint32_t SBO = 8 * PAIR_BK * 2;
@@ -446,16 +453,19 @@ tc_gather_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         for (int ks = 0; ks < ksteps; ++ks) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * PAIR_STAGE_BYTES);
-          const uint64_t adesc = make_smem_desc(sa, 16, SBO, LAYOUT_SW128);
-          const uint64_t bdesc = make_smem_desc(sa + PAIR_A_BYTES, 16, SBO, LAYOUT_SW128);
+          if (elect_one()) {
+            const uint32_t sa = smem_u32(smem + stage * PAIR_STAGE_BYTES);
+            const uint64_t adesc = make_smem_desc(sa, 16, SBO, LAYOUT_SW128);
+            const uint64_t bdesc = make_smem_desc(sa + PAIR_A_BYTES, 16, SBO, LAYOUT_SW128);
 #pragma unroll
-          for (int k = 0; k < PAIR_BK / 16; ++k)
-            umma_bf16_pair(acc, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (ks > 0 || k > 0) ? 1u : 0u);
-          umma_commit_pair(&empty_bar[stage], 3);
+            for (int k = 0; k < PAIR_BK / 16; ++k)
+              umma_bf16_pair(acc, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (ks > 0 || k > 0) ? 1u : 0u);
+            umma_commit_pair(&empty_bar[stage], 3);
+            if (ks == ksteps - 1) umma_commit_pair(&tmem_full[ti], 3);
+          }
+          __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit_pair(&tmem_full[ti], 3);
       }
     }
   } else {
@@ -556,43 +566,47 @@ tc_rp3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
-      // ===== TMA producer: the weight pack once, then one patch per tile =====
+    // ===== TMA producer: the weight pack once, then one patch per tile (converged warp, elected lane issues) =====
+    if (elect_one()) {
       mbar_expect_tx(w_bar, R.w_tx_bytes);
       for (int t = 0; t < P.ntaps; ++t)
         for (int kc = 0; kc < P.kchunks; ++kc) {
           const int wt = P.twi[t] * P.kchunks + kc;
           tma_load_3d(wsm + (size_t)wt * R.wtile_bytes, &tmB, w_bar, 0, c0, wt);
         }
-      int i = 0;
-      for (int tile = blockIdx.x; tile < R.tiles_total; tile += gridDim.x, ++i) {
-        const int stage = i % S;
-        const uint32_t phase = (uint32_t)(i / S) & 1u;
-        int t = tile;
-        const int tx = t % P.tiles_x; t /= P.tiles_x;
-        const int ty = t % P.tiles_y;
-        const int x0 = tx * RP_TW, y0 = ty * RP_TH, n0 = t / P.tiles_y;
-        mbar_wait(&empty_bar[stage], phase ^ 1);
+    }
+    __syncwarp();
+    int i = 0;
+    for (int tile = blockIdx.x; tile < R.tiles_total; tile += gridDim.x, ++i) {
+      const int stage = i % S;
+      const uint32_t phase = (uint32_t)(i / S) & 1u;
+      int t = tile;
+      const int tx = t % P.tiles_x; t /= P.tiles_x;
+      const int ty = t % P.tiles_y;
+      const int x0 = tx * RP_TW, y0 = ty * RP_TH, n0 = t / P.tiles_y;
+      mbar_wait(&empty_bar[stage], phase ^ 1);
+      if (elect_one()) {
         mbar_expect_tx(&full_bar[stage], (uint32_t)P.kchunks * (uint32_t)(R.pw * R.ph) * ROWB);
         for (int kc = 0; kc < P.kchunks; ++kc)
           tma_load_4d(psm + (size_t)stage * stage_bytes + (size_t)kc * R.patch_bytes, &tmA, &full_bar[stage], kc * BK,
                       x0 + R.dx_min, y0 + R.dy_min, n0);
       }
+      __syncwarp();
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ===== MMA issuer =====
-      constexpr uint32_t idesc = make_idesc_bf16(BM, BN, 0, 0);
-      const uint32_t sbo_a = (uint32_t)R.pw * ROWB;       // 8-row groups = consecutive tile rows, PW pixels apart
-      mbar_wait(w_bar, 0);
-      int i = 0;
-      for (int tile = blockIdx.x; tile < R.tiles_total; tile += gridDim.x, ++i) {
-        const int stage = i % S, a = i % NA;
-        const uint32_t sphase = (uint32_t)(i / S) & 1u, aphase = (uint32_t)(i / NA) & 1u;
-        const uint32_t acc = tmem_base + (uint32_t)a * ACC_COLS;
-        mbar_wait(&tmem_empty[a], aphase ^ 1);            // the epilogue has drained this accumulator
-        mbar_wait(&full_bar[stage], sphase);
-        tc_fence_after();
+    // ===== MMA issuer =====
+    constexpr uint32_t idesc = make_idesc_bf16(BM, BN, 0, 0);
+    const uint32_t sbo_a = (uint32_t)R.pw * ROWB;       // 8-row groups = consecutive tile rows, PW pixels apart
+    mbar_wait(w_bar, 0);
+    int i = 0;
+    for (int tile = blockIdx.x; tile < R.tiles_total; tile += gridDim.x, ++i) {
+      const int stage = i % S, a = i % NA;
+      const uint32_t sphase = (uint32_t)(i / S) & 1u, aphase = (uint32_t)(i / NA) & 1u;
+      const uint32_t acc = tmem_base + (uint32_t)a * ACC_COLS;
+      mbar_wait(&tmem_empty[a], aphase ^ 1);            // the epilogue has drained this accumulator
+      mbar_wait(&full_bar[stage], sphase);
+      tc_fence_after();
+      if (elect_one()) {
         uint32_t first = 0;
         for (int kc = 0; kc < P.kchunks; ++kc) {
           const uint32_t pa = smem_u32(psm + (size_t)stage * stage_bytes + (size_t)kc * R.patch_bytes);
@@ -611,6 +625,7 @@ tc_rp3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
         umma_commit(&empty_bar[stage]);
         umma_commit(&tmem_full[a]);
       }
+      __syncwarp();
     }
   } else {
     // ===== epilogue: warps 2..5, TMEM lanes 32*(warp%4) .. +31; lane m of the tile = pixel (m % 8, m / 8) =====
@@ -861,7 +876,10 @@ static bool tc_view_ok(const nemar_tensor* t, bool allow_f32) {
 }
 
 static int gather_bn(int cd, int bk, bool f32) {
-  static const int wide = [] { const char* e = getenv("NEMAR_TC_WIDE"); return e ? atoi(e) : 0; }();
+  // 256-channel destination tiles (one CTA per SM, 48 KB per 128x256x64 step instead of 2 x 32 KB): measured with the
+  // round-2 epilogue 84 / 76 us against 94 / 85 us (fprop / dgrad of the 256 -> 256 ResnetBlock conv); NEMAR_TC_WIDE=0
+  // selects the 128-wide tiles
+  static const int wide = [] { const char* e = getenv("NEMAR_TC_WIDE"); return e ? atoi(e) : 1; }();
   if (wide && cd % 256 == 0 && bk == 64 && !f32) return 256;
   return (cd % 128 == 0) ? 128 : ((cd % 64 == 0) ? 64 : ((cd % 32 == 0) ? 32 : 16));
 }
@@ -942,7 +960,9 @@ int tc_gather_gemm(const nemar_tensor* src_in, const nemar_tensor* dst_in, const
     static const int stag = [] { const char* e = getenv("NEMAR_TC_STAGGER"); return e ? atoi(e) : 0; }();   // measured: no effect on B200 (not an L2 hot-spot problem)
     P.kstagger = stag;
     P.stats = nullptr;
-    static const int rp3_env = [] { const char* e = getenv("NEMAR_TC_RP3"); return e ? atoi(e) : 0; }();
+    // resident-patch kernel for stride-1 k x k layers with <= 64 output channels: default since the converged-warp issue
+    // fix (32 -> 32 @256^2: 75 us against 119 us tiled; 96 -> 32: 146 / 182 against 250 / 295); NEMAR_TC_RP3=0 disables
+    static const int rp3_env = [] { const char* e = getenv("NEMAR_TC_RP3"); return e ? atoi(e) : 1; }();
     if (rp3_env && !pair && gg.sm == 1 && gg.sd == 1) {
       Rp3Params R;
       size_t rp_smem = 0;
@@ -980,8 +1000,7 @@ int tc_gather_gemm(const nemar_tensor* src_in, const nemar_tensor* dst_in, const
   }
   if (stats) {
     // InstanceNorm statistics of the (L2-resident) output: separate reduction pass
-    cudaMemsetAsync(stats, 0, sizeof(float) * 2 * (size_t)dst.n * dst.c, s);
-    return nemar_instnorm_stats(dst_in, stats, (void*)s);
+    return nemar_instnorm_stats(dst_in, stats, (void*)s);        // accumulates: the caller hands in zeroed stats
   }
   return 0;
 }
@@ -1059,15 +1078,16 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant_
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
-      int stage = 0; uint32_t phase = 0;
-      for (int ks = 0; ks < ksteps; ++ks) {
-        int t = t_lo + ks;
-        const int tx = t % P.tiles_x; t /= P.tiles_x;
-        const int ty = t % P.tiles_y;
-        const int tn = t / P.tiles_y;
-        const int x0 = tx * P.tw, y0 = ty * P.th, n0 = tn * P.tn;
-        mbar_wait(&empty_bar[stage], phase ^ 1);
+    // ===== TMA producer (converged warp, elected lane issues: see tc_gather_kernel) =====
+    int stage = 0; uint32_t phase = 0;
+    for (int ks = 0; ks < ksteps; ++ks) {
+      int t = t_lo + ks;
+      const int tx = t % P.tiles_x; t /= P.tiles_x;
+      const int ty = t % P.tiles_y;
+      const int tn = t / P.tiles_y;
+      const int x0 = tx * P.tw, y0 = ty * P.th, n0 = tn * P.tn;
+      mbar_wait(&empty_bar[stage], phase ^ 1);
+      if (elect_one()) {
         uint8_t* sa = smem + stage * P.stage_bytes;
         // channel chunks of the M operand beyond its extent feed accumulator rows nobody reads: their loads are
         // skipped, and when the whole M operand is narrower than 128 channels the stage does not even reserve room
@@ -1084,19 +1104,20 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant_
 #pragma unroll
         for (int c = 0; c < Cfg::NB; ++c)
           tma_load_4d(sa + P.a_bytes + c * Cfg::CHUNK_B, &tmX, &full_bar[stage], cit * BN + c * CB, xb, yb, n0);
-        if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
+      __syncwarp();
+      if (++stage == STAGES) { stage = 0; phase ^= 1; }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(BM, BN, 1, 1);
-      // MN-major: CA (CB) channels per swizzled row; LBO = distance between channel chunks (one TMA box),
-      // SBO = distance between 8-pixel K groups; one UMMA consumes 16 pixels
-      constexpr uint32_t SBO_A = 8 * CA * 2, SBO_B = 8 * CB * 2, KADV_A = (16 * CA * 2) >> 4, KADV_B = (16 * CB * 2) >> 4;
-      int stage = 0; uint32_t phase = 0;
-      for (int ks = 0; ks < ksteps; ++ks) {
-        mbar_wait(&full_bar[stage], phase);
-        tc_fence_after();
+    constexpr uint32_t idesc = make_idesc_bf16(BM, BN, 1, 1);
+    // MN-major: CA (CB) channels per swizzled row; LBO = distance between channel chunks (one TMA box),
+    // SBO = distance between 8-pixel K groups; one UMMA consumes 16 pixels
+    constexpr uint32_t SBO_A = 8 * CA * 2, SBO_B = 8 * CB * 2, KADV_A = (16 * CA * 2) >> 4, KADV_B = (16 * CB * 2) >> 4;
+    int stage = 0; uint32_t phase = 0;
+    for (int ks = 0; ks < ksteps; ++ks) {
+      mbar_wait(&full_bar[stage], phase);
+      tc_fence_after();
+      if (elect_one()) {
         const uint32_t sa = smem_u32(smem + stage * P.stage_bytes);
         const uint64_t adesc = make_smem_desc(sa, Cfg::CHUNK_A, SBO_A, layout_for(CA));
         const uint64_t bdesc = make_smem_desc(sa + P.a_bytes, Cfg::CHUNK_B, SBO_B, layout_for(CB));
@@ -1105,9 +1126,10 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant_
           umma_bf16(tmem_base, adesc + (uint64_t)(k * KADV_A), bdesc + (uint64_t)(k * KADV_B), idesc,
                     (ks > 0 || k > 0) ? 1u : 0u);
         umma_commit(&empty_bar[stage]);
-        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        if (ks == ksteps - 1) umma_commit(tmem_full);
       }
-      umma_commit(tmem_full);
+      __syncwarp();
+      if (++stage == STAGES) { stage = 0; phase ^= 1; }
     }
   } else {
     const int q = warp & 3;
@@ -1195,16 +1217,17 @@ tc_wgrad_pair_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_cons
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
-      const uint32_t full_leader = mapa_u32(smem_u32(&full_bar[0]), 0);
-      int stage = 0; uint32_t phase = 0;
-      for (int ks = 0; ks < ksteps; ++ks) {
-        int t = t_lo + ks;
-        const int tx = t % P.tiles_x; t /= P.tiles_x;
-        const int ty = t % P.tiles_y;
-        const int tn = t / P.tiles_y;
-        const int x0 = tx * P.tw, y0 = ty * P.th, n0 = tn * P.tn;
-        mbar_wait(&empty_bar[stage], phase ^ 1);
+    // ===== TMA producer (both CTAs; converged warp, elected lane issues) =====
+    const uint32_t full_leader = mapa_u32(smem_u32(&full_bar[0]), 0);
+    int stage = 0; uint32_t phase = 0;
+    for (int ks = 0; ks < ksteps; ++ks) {
+      int t = t_lo + ks;
+      const int tx = t % P.tiles_x; t /= P.tiles_x;
+      const int ty = t % P.tiles_y;
+      const int tn = t / P.tiles_y;
+      const int x0 = tx * P.tw, y0 = ty * P.th, n0 = tn * P.tn;
+      mbar_wait(&empty_bar[stage], phase ^ 1);
+      if (elect_one()) {
         uint8_t* sa = smem + stage * WGP_STAGE_BYTES;
         if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * WGP_STAGE_BYTES);
         const uint32_t fb = full_leader + (uint32_t)stage * 8u;
@@ -1214,27 +1237,31 @@ tc_wgrad_pair_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_cons
 #pragma unroll
         for (int c = 0; c < 2; ++c)
           tma_load_4d_pair(sa + WGP_A_BYTES + c * WGP_CHUNK, &tmX, fb, cit * 256 + (int)rank * 128 + c * 64, xs, ys, n0);
-        if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
+      __syncwarp();
+      if (++stage == STAGES) { stage = 0; phase ^= 1; }
     }
   } else if (warp == 1) {
-    if (lane == 0 && rank == 0) {
+    if (rank == 0) {
       constexpr uint32_t idesc = make_idesc_bf16(2 * BM, 256, 1, 1);
       constexpr uint32_t SBO = 8 * 64 * 2, KADV = (16 * 64 * 2) >> 4;
       int stage = 0; uint32_t phase = 0;
       for (int ks = 0; ks < ksteps; ++ks) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
-        const uint32_t sa = smem_u32(smem + stage * WGP_STAGE_BYTES);
-        const uint64_t adesc = make_smem_desc(sa, WGP_CHUNK, SBO, LAYOUT_SW128);
-        const uint64_t bdesc = make_smem_desc(sa + WGP_A_BYTES, WGP_CHUNK, SBO, LAYOUT_SW128);
+        if (elect_one()) {
+          const uint32_t sa = smem_u32(smem + stage * WGP_STAGE_BYTES);
+          const uint64_t adesc = make_smem_desc(sa, WGP_CHUNK, SBO, LAYOUT_SW128);
+          const uint64_t bdesc = make_smem_desc(sa + WGP_A_BYTES, WGP_CHUNK, SBO, LAYOUT_SW128);
 #pragma unroll
-        for (int k = 0; k < WG_KP / 16; ++k)
-          umma_bf16_pair(tmem_base, adesc + (uint64_t)(k * KADV), bdesc + (uint64_t)(k * KADV), idesc, (ks > 0 || k > 0) ? 1u : 0u);
-        umma_commit_pair(&empty_bar[stage], 3);
+          for (int k = 0; k < WG_KP / 16; ++k)
+            umma_bf16_pair(tmem_base, adesc + (uint64_t)(k * KADV), bdesc + (uint64_t)(k * KADV), idesc, (ks > 0 || k > 0) ? 1u : 0u);
+          umma_commit_pair(&empty_bar[stage], 3);
+          if (ks == ksteps - 1) umma_commit_pair(tmem_full, 3);
+        }
+        __syncwarp();
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
-      umma_commit_pair(tmem_full, 3);
     }
   } else {
     const int q = warp & 3;

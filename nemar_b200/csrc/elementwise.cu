@@ -752,10 +752,42 @@ norm_act_bwd_apply_kernel(TView x, const float* __restrict__ stats, int act, TVi
   }
 }
 
+// zero the halo ring of a padded view (the interior is left alone): grid (chunks, n)
+template <typename T> __global__ void zero_halo_kernel(TView t) {
+  const int nn = blockIdx.y, p = t.pad;
+  const int ring = 2 * p * t.wp + 2 * p * t.h;            // halo pixels of one sample
+  const int64_t total = (int64_t)ring * t.c;
+  T* base = (T*)t.ptr + (int64_t)nn * t.hp * t.wp * t.cs + t.coff;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int ch = (int)(i % t.c);
+    int r = (int)(i / t.c), yp, xp;
+    if (r < 2 * p * t.wp) {                                // top and bottom rows, full width
+      const int row = r / t.wp;
+      xp = r - row * t.wp;
+      yp = row < p ? row : t.h + row;                      // rows p .. 2p-1 map to the bottom block
+    } else {                                               // left and right columns of the interior rows
+      r -= 2 * p * t.wp;
+      const int row = r / (2 * p), k = r - row * (2 * p);
+      yp = p + row;
+      xp = k < p ? k : t.w + k;
+    }
+    base[((int64_t)yp * t.wp + xp) * t.cs + ch] = from_f<T>(0.f);
+  }
+}
+
 NEMAR_API int nemar_norm_act_bwd_apply(const nemar_tensor* x, const float* stats, int act,
                                        const nemar_tensor* dy, int pad_mode, const float* red,
-                                       const nemar_tensor* dx, const nemar_tensor* dres, int dres_accumulate,
+                                       const nemar_tensor* dx, const nemar_tensor* dres, int flags,
                                        float* db, void* stream) {
+  const int dres_accumulate = flags & 1;          // dres += fold(dy) instead of =
+  const bool db_accumulate = (flags & 2) != 0;    // db += column sums (caller's running total) instead of =
+  const bool zero_dres_halo = (flags & 4) != 0;   // the halo ring of dres is zeroed here (the passes write its interior)
+  if (dres && zero_dres_halo && dres->pad > 0 && view_ok(dres)) {
+    TView dv = make_view(dres);
+    const int64_t ring_items = (int64_t)(2 * dv.pad * dv.wp + 2 * dv.pad * dv.h) * dv.c;
+    DISPATCH_DTYPE(dv.dtype, T, (zero_halo_kernel<T><<<dim3(grid_for(ring_items, 256, 8), dv.n), 256, 0, (cudaStream_t)stream>>>(dv)));
+    NEMAR_LAUNCH_CHECK();
+  }
   NEMAR_REQUIRE(view_ok(x) && view_ok(dy) && view_ok(dx) && same_shape(x, dy) && same_shape(x, dx) &&
                     x->dtype == dy->dtype && x->dtype == dx->dtype,
                 "norm_act_bwd_apply: mismatch");
@@ -766,7 +798,7 @@ NEMAR_API int nemar_norm_act_bwd_apply(const nemar_tensor* x, const float* stats
   const float inv_hw = 1.f / ((float)xv.h * (float)xv.w);
   cudaStream_t s = (cudaStream_t)stream;
   if ((nlean::enabled_mask() & 8) && nfast::eligible(x) && nfast::eligible(dy) && nfast::eligible(dx) && (!dres || nfast::eligible(dres))) {
-    if (db) cudaMemsetAsync(db, 0, sizeof(float) * xv.c, s);
+    if (db && !db_accumulate) cudaMemsetAsync(db, 0, sizeof(float) * xv.c, s);
     dim3 grid(nlean::chunks_for((int64_t)xv.h * xv.w, xv.c / 8, xv.n, false, true), xv.n);
     NLEAN_ACT_SWITCH(act, (nlean::bwd_apply_kernel<A><<<grid, 256, sizeof(float) * 5 * xv.c, s>>>(
         xv, stats, act, dyv, pad_mode, red, dxv, dr, dres != nullptr, dres_accumulate, inv_hw, db)));
@@ -775,7 +807,7 @@ NEMAR_API int nemar_norm_act_bwd_apply(const nemar_tensor* x, const float* stats
   }
   static const bool fast_apply = [] { const char* e = getenv("NEMAR_NORM_FAST_ALL"); return e && atoi(e); }();
   if (fast_apply && nfast::eligible(x) && nfast::eligible(dy) && nfast::eligible(dx) && (!dres || nfast::eligible(dres))) {
-    if (db) cudaMemsetAsync(db, 0, sizeof(float) * xv.c, s);
+    if (db && !db_accumulate) cudaMemsetAsync(db, 0, sizeof(float) * xv.c, s);
     dim3 grid(nfast::chunks_for((int64_t)xv.h * xv.w, xv.c / 8, xv.n), xv.n);
     nfast::bwd_apply_kernel<<<grid, 256, sizeof(float) * xv.c, s>>>(xv, stats, act, dyv, pad_mode, red, dxv, dr,
                                                                      dres != nullptr, dres_accumulate, inv_hw, db);
@@ -786,7 +818,7 @@ NEMAR_API int nemar_norm_act_bwd_apply(const nemar_tensor* x, const float* stats
     constexpr int VV = VecTraits<T>::V;
     bool vec = view_vec_ok<T>(x) && view_vec_ok<T>(dy) && view_vec_ok<T>(dx) && (!dres || view_vec_ok<T>(dres));
     size_t smem = db ? sizeof(float) * xv.c : 0;
-    if (db) cudaMemsetAsync(db, 0, sizeof(float) * xv.c, s);
+    if (db && !db_accumulate) cudaMemsetAsync(db, 0, sizeof(float) * xv.c, s);
     if (vec) {
       int64_t items = (int64_t)xv.h * xv.w * (xv.c / VV);
       norm_act_bwd_apply_kernel<T, VV><<<dim3(plane_chunks(items, xv.n), xv.n), 256, smem, s>>>(
@@ -1112,7 +1144,10 @@ __device__ __forceinline__ uint64_t splitmix64(uint64_t z) {
   return z ^ (z >> 31);
 }
 
-template <typename T> __global__ void dropout_kernel(TView x, TView y, uint64_t seed, uint64_t offset) {
+// `step`: optional device-resident step counter; the mask of a replayed CUDA graph then changes from step to step
+template <typename T> __global__ void dropout_kernel(TView x, TView y, uint64_t seed, uint64_t offset,
+                                                     const int64_t* __restrict__ step) {
+  if (step) offset += (uint64_t)(*step) * 0x9E3779B97F4A7C15ull;
   const int64_t total = (int64_t)x.n * x.h * x.w * x.c;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
        i += (int64_t)gridDim.x * blockDim.x) {
@@ -1127,13 +1162,32 @@ template <typename T> __global__ void dropout_kernel(TView x, TView y, uint64_t 
   }
 }
 
-NEMAR_API int nemar_dropout(const nemar_tensor* x, const nemar_tensor* y, uint64_t seed, uint64_t offset,
-                            void* stream) {
+static int dropout_impl(const nemar_tensor* x, const nemar_tensor* y, uint64_t seed, uint64_t offset, const int64_t* step,
+                        void* stream) {
   NEMAR_REQUIRE(view_ok(x) && view_ok(y) && same_shape(x, y) && x->dtype == y->dtype, "dropout: mismatch");
   TView xv = make_view(x), yv = make_view(y);
   int64_t total = (int64_t)xv.n * xv.h * xv.w * xv.c;
   DISPATCH_DTYPE(xv.dtype, T, (dropout_kernel<T><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
-                                  xv, yv, seed, offset)));
+                                  xv, yv, seed, offset, step)));
+  NEMAR_LAUNCH_CHECK();
+  return 0;
+}
+
+NEMAR_API int nemar_dropout(const nemar_tensor* x, const nemar_tensor* y, uint64_t seed, uint64_t offset,
+                            void* stream) {
+  return dropout_impl(x, y, seed, offset, nullptr, stream);
+}
+
+NEMAR_API int nemar_dropout_dev(const nemar_tensor* x, const nemar_tensor* y, uint64_t seed, uint64_t salt,
+                                const int64_t* step_dev, void* stream) {
+  NEMAR_REQUIRE(step_dev, "dropout_dev: step counter");
+  return dropout_impl(x, y, seed, salt, step_dev, stream);
+}
+
+__global__ void counter_add_kernel(int64_t* c, int64_t v) { *c += v; }
+NEMAR_API int nemar_counter_add(int64_t* counter_dev, int64_t v, void* stream) {
+  NEMAR_REQUIRE(counter_dev, "counter_add: pointer");
+  counter_add_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(counter_dev, v);
   NEMAR_LAUNCH_CHECK();
   return 0;
 }

@@ -27,10 +27,20 @@ class DevicePrefetcher:
         s = self.slots[i]
         shapes = {k: (tuple(batch[k].shape), batch[k].dtype) for k in self.keys}
         if s is None or s["shapes"] != shapes:
+            # New device buffers are FIRST WRITTEN on the side stream.  The caching allocator may hand out memory that
+            # pending work on the compute stream still reads or writes (a freed temporary of a step that has not run
+            # yet), so the side stream is ordered behind everything enqueued so far, and the buffers are taken from the
+            # side stream's own pool.  (Rare: the first `depth` batches and shape changes.)
+            self.stream.wait_stream(torch.cuda.current_stream(self.device))
+            if s is not None and s["busy"] is not None:
+                s["busy"].synchronize()
             s = {"shapes": shapes, "pin": {}, "dev": {}, "free": None, "busy": None}
-            for k in self.keys:
-                s["pin"][k] = torch.empty(batch[k].shape, dtype=batch[k].dtype, pin_memory=True)
-                s["dev"][k] = torch.empty(batch[k].shape, dtype=batch[k].dtype, device=self.device)
+            with torch.cuda.stream(self.stream):
+                for k in self.keys:
+                    # pinned staging only for pageable sources (cudaHostAlloc costs ~10 ms per buffer)
+                    s["pin"][k] = None if batch[k].is_pinned() else torch.empty(batch[k].shape, dtype=batch[k].dtype, pin_memory=True)
+                    s["dev"][k] = torch.empty(batch[k].shape, dtype=batch[k].dtype, device=self.device)
+                    s["dev"][k].record_stream(torch.cuda.current_stream(self.device))
             self.slots[i] = s
         return s
 
@@ -44,6 +54,8 @@ class DevicePrefetcher:
             for k in self.keys:
                 src = batch[k]
                 if not src.is_pinned():
+                    if s["pin"][k] is None:
+                        s["pin"][k] = torch.empty(src.shape, dtype=src.dtype, pin_memory=True)
                     if s["busy"] is not None:
                         s["busy"].synchronize()          # the previous H2D out of this pinned buffer has completed
                     s["pin"][k].copy_(src)

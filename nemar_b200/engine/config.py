@@ -7,6 +7,8 @@ class EngineConfig:
         self.precision = "bf16"      # storage dtype of activations / packed weights: "bf16" | "fp32"
         self.conv_engine = "auto"    # "auto": tcgen05 where supported, else generic; "generic": CUDA cores only
         self.dropout_seed = 0x5EED
+        self.step_dev = None         # device-resident step counter (int64[1]) read by the dropout kernels
+        self.dropout_calls = 0       # dropout call sites seen since the step began (-> a distinct salt per site)
 
     @property
     def dtype(self):
@@ -14,6 +16,13 @@ class EngineConfig:
 
 
 CONFIG = EngineConfig()
+
+
+def step_counter(device):
+    """The device-resident step counter (created on first use)."""
+    if CONFIG.step_dev is None or CONFIG.step_dev.device != torch.device(device):
+        CONFIG.step_dev = torch.zeros(1, dtype=torch.int64, device=device)
+    return CONFIG.step_dev
 
 
 def configure(precision=None, conv_engine=None):

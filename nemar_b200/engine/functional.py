@@ -27,6 +27,42 @@ def _c(t):
     return t if t.is_contiguous() else t.contiguous()
 
 
+class _ZeroArena:
+    """One pre-zeroed fp32 buffer per training step for the many small accumulators of the path (InstanceNorm
+    statistics and backward sums of ~80 layers, loss scalars): ONE fill per step instead of ~250 torch.zeros launches.
+    Active only between begin_step() and end_step(); outside a step (direct op calls, inference) zeros() falls back to
+    torch.zeros.  Slices live until the next begin_step — i.e. for the step whose autograd graph holds them."""
+
+    def __init__(self):
+        self.buf, self.pos, self.high, self.active = None, 0, 0, False
+
+    def begin(self, device):
+        if self.buf is None or self.buf.device != torch.device(device):
+            self.buf = torch.zeros(8 << 20, dtype=torch.float32, device=device)      # 32 MB
+            self.high = 0
+        elif self.high > 0:
+            self.buf[:self.high].zero_()
+        self.pos, self.active = 0, True
+
+    def end(self):
+        self.active = False
+
+    def zeros(self, shape, device):
+        n = 1
+        for d in shape:
+            n *= int(d)
+        n4 = (n + 3) // 4 * 4
+        if not self.active or self.buf.device != torch.device(device) or self.pos + n4 > self.buf.numel():
+            return torch.zeros(shape, dtype=torch.float32, device=device)
+        t = self.buf[self.pos:self.pos + n].view(shape)
+        self.pos += n4
+        self.high = max(self.high, self.pos)
+        return t
+
+
+ARENA = _ZeroArena()
+
+
 def _deliver(param, grad):
     """Hand a parameter gradient over.  When the parameter already owns a gradient buffer (the optimizer's flat
     bucket), accumulate into it HERE, on the stream this backward runs on, and tell autograd there is nothing left
@@ -205,35 +241,106 @@ class ConvCfg:
         return f(h), f(w)
 
 
+class _PackJob(L.C.Structure):
+    _fields_ = [("w", L.C.c_void_p), ("out", L.C.c_void_p), ("O", L.C.c_int32), ("op", L.C.c_int32), ("I", L.C.c_int32),
+                ("ip", L.C.c_int32), ("kh", L.C.c_int32), ("kw", L.C.c_int32), ("w_is_oi", L.C.c_int32), ("flip", L.C.c_int32),
+                ("dtype", L.C.c_int32), ("kind", L.C.c_int32)]
+
+
+import weakref  # noqa: E402
+
+_PACK_OWNERS = weakref.WeakSet()      # every live PackedWeights (they die with their Conv module)
+_PACK_PLANS = {}                      # flat buffer address -> (key, jobs tensor, blocks tensor, nblocks)
+
+
 class PackedWeights:
-    """Per-parameter cache of the forward / backward packs and the padded bias (rebuilt when the weights epoch
-    changes or the layer is called with another channel padding)."""
+    """Per-parameter cache of the forward / backward packs and the padded bias.  The pack BUFFERS are allocated once
+    and refreshed in place: lazily by a per-layer call when the entry is stale (first use, load_state_dict, any foreign
+    in-place write), or — on the training path — by ONE multi-tensor launch per optimizer step (refresh_packs)."""
 
     def __init__(self):
         self.cache = {}
+        _PACK_OWNERS.add(self)
 
-    def get(self, weight, bias, cfg, dtype, cin_p):
+    @staticmethod
+    def _stamp(weight, bias, owner):
+        # epoch: bumped by the engine's loaders / init; _version catches any other in-place write through torch;
+        # the flat Adam kernel writes through raw pointers and refreshes the packs itself (refresh_packs)
+        src = owner if owner is not None else weight
+        return (weights_epoch(), src.data_ptr(), src._version, bias._version if bias is not None else 0)
+
+    def get(self, weight, bias, cfg, dtype, cin_p, owner=None):
+        """owner: the Parameter the weight tensor was derived from (tap-transformed heads / tails); entries with an
+        owner are refreshed lazily only"""
         key = (dtype, cin_p, cfg.cout_p)
         ent = self.cache.get(key)
-        # (epoch bumped by the engine's own optimizer / loaders; _version catches any other in-place write — a foreign
-        #  load_state_dict, an EMA, a manual weight.copy_)
-        stamp = (weights_epoch(), weight.data_ptr(), weight._version, bias._version if bias is not None else 0)
-        if ent is None or ent[0] != stamp:
+        stamp = self._stamp(weight, bias, owner)
+        if ent is None:
             k2 = cfg.k * cfg.k
-            wf = torch.empty(cfg.cout_p * k2 * cin_p, dtype=dtype, device=weight.device)
-            wd = torch.empty(cin_p * k2 * cfg.cout_p, dtype=dtype, device=weight.device)
-            call("nemar_pack_weights", fptr(weight.detach()), cfg.geom, L.dtype_code(wf), cin_p, cfg.cout_p, vptr(wf),
-                 vptr(wd), stream())
-            bp = None
-            if bias is not None:
-                if cfg.cout_p == cfg.cout:
-                    bp = bias.detach()
-                else:
-                    bp = torch.zeros(cfg.cout_p, dtype=torch.float32, device=weight.device)
-                    bp[:cfg.cout].copy_(bias.detach())
-            ent = (stamp, wf, wd, bp)
+            ent = {"wf": torch.empty(cfg.cout_p * k2 * cin_p, dtype=dtype, device=weight.device),
+                   "wd": torch.empty(cin_p * k2 * cfg.cout_p, dtype=dtype, device=weight.device),
+                   "bp": None, "stamp": None, "cfg": cfg, "cin_p": cin_p, "weight": None, "bias": None, "derived": owner is not None}
+            if bias is not None and cfg.cout_p != cfg.cout:
+                ent["bp"] = torch.zeros(cfg.cout_p, dtype=torch.float32, device=weight.device)
             self.cache[key] = ent
-        return ent[1], ent[2], ent[3]
+        if ent["stamp"] != stamp:
+            call("nemar_pack_weights", fptr(weight.detach()), cfg.geom, L.dtype_code(ent["wf"]), cin_p, cfg.cout_p,
+                 vptr(ent["wf"]), vptr(ent["wd"]), stream())
+            if ent["bp"] is not None:
+                ent["bp"][:cfg.cout].copy_(bias.detach())
+            ent["stamp"] = stamp
+            ent["weight"] = (owner if owner is not None else weight)
+            ent["bias"] = bias
+        bp = ent["bp"] if ent["bp"] is not None else (bias.detach() if bias is not None else None)
+        return ent["wf"], ent["wd"], bp
+
+
+def _pack_jobs(ent):
+    """the nemar_pack_job records of one cache entry (same mapping as nemar_pack_weights, conv_api.cu)"""
+    cfg, cin_p, w = ent["cfg"], ent["cin_p"], ent["weight"]
+    code = L.dtype_code(ent["wf"])
+    t = bool(cfg.transposed)
+    jobs = [_PackJob(w.data_ptr(), ent["wf"].data_ptr(), cfg.cout, cfg.cout_p, cfg.cin, cin_p, cfg.k, cfg.k, 0 if t else 1, 1 if t else 0, code, 1),
+            _PackJob(w.data_ptr(), ent["wd"].data_ptr(), cfg.cin, cin_p, cfg.cout, cfg.cout_p, cfg.k, cfg.k, 1 if t else 0, 0 if t else 1, code, 1)]
+    if ent["bp"] is not None:
+        jobs.append(_PackJob(ent["bias"].data_ptr(), ent["bp"].data_ptr(), cfg.cout, cfg.cout_p, 1, 1, 1, 1, 1, 0, L.F32, 2))
+    return jobs
+
+
+def refresh_packs(flat_p):
+    """After an optimizer step: re-pack, in ONE launch, every cached weight pack whose parameter lives in `flat_p`
+    (the optimizer's flat buffer), and mark those entries current.  Entries derived from a parameter through a host-side
+    transform (k7 heads / tails) are invalidated instead and re-packed by their next use."""
+    lo = flat_p.data_ptr()
+    hi = lo + flat_p.numel() * 4
+    ents = []
+    for owner in list(_PACK_OWNERS):
+        for ent in owner.cache.values():
+            w = ent["weight"]
+            if w is None or not (lo <= w.data_ptr() < hi):
+                continue
+            if ent["derived"]:
+                ent["stamp"] = None
+            else:
+                ents.append(ent)
+    if not ents:
+        return
+    key = tuple((id(e), e["wf"].data_ptr(), e["weight"].data_ptr()) for e in ents)
+    plan = _PACK_PLANS.get(lo)
+    if plan is None or plan[0] != key:
+        jobs = [j for e in ents for j in _pack_jobs(e)]
+        blocks = []
+        for ji, j in enumerate(jobs):
+            total = j.op * j.kh * j.kw * j.ip
+            blocks += [(ji, b) for b in range((total + 2047) // 2048)]
+        arr = (_PackJob * len(jobs))(*jobs)
+        jt = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(flat_p.device)
+        bt = torch.tensor(blocks, dtype=torch.int32).reshape(-1).to(flat_p.device)
+        plan = (key, jt, bt, len(blocks))
+        _PACK_PLANS[lo] = plan
+    call("nemar_pack_weights_multi", vptr(plan[1]), vptr(plan[2]), plan[3], stream())
+    for e in ents:
+        e["stamp"] = PackedWeights._stamp(e["weight"], e["bias"], None)
 
 
 def _cast(t, dtype):
@@ -244,17 +351,17 @@ def _cast(t, dtype):
 
 class Conv2dFn(Function):
     @staticmethod
-    def forward(ctx, x, weight, bias, cfg, packed):
+    def forward(ctx, x, weight, bias, cfg, packed, owner=None):
         x = _c(x)
         n, hp, wp, cin_p = x.shape
         h, w = hp - 2 * cfg.x_pad, wp - 2 * cfg.x_pad
         ho, wo = cfg.out_hw(h, w)
-        wf, wd, bp = packed.get(weight, bias, cfg, x.dtype, cin_p)
+        wf, wd, bp = packed.get(weight, bias, cfg, x.dtype, cin_p, owner)
         ydt = torch.float32 if cfg.out_f32 else x.dtype
         y = torch.empty((n, ho, wo, cfg.cout_p), dtype=ydt, device=x.device)
         stats = None
         if cfg.stats:
-            stats = torch.zeros((n, cfg.cout_p, 2), dtype=torch.float32, device=x.device)
+            stats = ARENA.zeros((n, cfg.cout_p, 2), x.device)
         # while the conv launches are being timed (bench.py's roofline pass) the InstanceNorm statistics pass is issued
         # as its own call, so that the events around nemar_conv2d_fprop bracket the convolution kernel alone; it is the
         # same kernel on the same buffers that nemar_conv2d_fprop launches itself when handed `stats`
@@ -304,7 +411,7 @@ class Conv2dFn(Function):
             db = torch.empty(cfg.cout_p, dtype=torch.float32, device=x.device)
             call("nemar_bias_grad", view(g), fptr(db), stream())
             db = _deliver(ctx.bias_param, db[:cfg.cout])
-        return dx, dw, db, None, None
+        return dx, dw, db, None, None, None
 
 
 class TapsWeightFn(Function):
@@ -418,21 +525,28 @@ class NormActFn(Function):
         n, h, w, c = x.shape
         red = None
         if stats is not None:
-            red = torch.zeros((n, c, 2), dtype=torch.float32, device=x.device)
+            red = ARENA.zeros((n, c, 2), x.device)
             call("nemar_norm_act_bwd_reduce", view(x), fptr(stats), act, view(dy, out_pad), pad_mode, fptr(red),
                  stream())
         dx = torch.empty_like(x)
-        dres, drv = None, None
+        dres, drv, flags = None, None, 0
         if res_shape is not None and ctx.needs_input_grad[2]:
-            dres = (torch.zeros if res_pad > 0 else torch.empty)(res_shape, dtype=x.dtype, device=x.device)
+            dres = torch.empty(res_shape, dtype=x.dtype, device=x.device)
             drv = view(dres, res_pad)
-        # the bias gradient of the conv that produced x is the column sum of dx: fused into this pass
-        db = None
-        if nbias and ctx.needs_input_grad[7]:
-            db = torch.empty(c, dtype=torch.float32, device=x.device)
+            if res_pad > 0:
+                flags |= 4                      # the pass zeroes the halo ring of dres (it writes only the interior)
+        # the bias gradient of the conv that produced x is the column sum of dx: fused into this pass, and accumulated
+        # straight into the optimizer's gradient bucket when the parameter owns one
+        db, bias, direct = None, ctx.bias_param, False
+        if nbias and ctx.needs_input_grad[7] and bias.requires_grad:
+            direct = bias.is_leaf and bias.grad is not None and nbias == c and bias.grad.is_contiguous()
+            db = bias.grad if direct else torch.empty(c, dtype=torch.float32, device=x.device)
+            if direct:
+                flags |= 2
         call("nemar_norm_act_bwd_apply", view(x), fptr(stats), act, view(dy, out_pad), pad_mode, fptr(red), view(dx),
-             drv, 0, fptr(db), stream())
-        return dx, None, dres, None, None, None, None, _deliver(ctx.bias_param, db[:nbias] if db is not None else None)
+             drv, flags, fptr(db), stream())
+        dbias = None if (db is None or direct) else _deliver(bias, db[:nbias])
+        return dx, None, dres, None, None, None, None, dbias
 
 
 class MaxPool2Fn(Function):
@@ -496,20 +610,39 @@ class ResizeNCHWFn(Function):
 
 
 class DropoutFn(Function):
+    """Dropout(0.5) (networks.py:427-428).  The mask is a hash of (seed, salt, step): `salt` identifies the call site
+    within a step (host constant), the step number is read by the kernel from device memory, so a captured step draws
+    a fresh mask on every replay and the backward pass regenerates the forward's mask."""
+
     @staticmethod
-    def forward(ctx, x, seed, offset):
+    def forward(ctx, x, seed, salt, step_dev):
         x = _c(x)
         y = torch.empty_like(x)
-        call("nemar_dropout", view(x), view(y), L.u64(seed), L.u64(offset), stream())
-        ctx.meta = (seed, offset)
+        call("nemar_dropout_dev", view(x), view(y), L.u64(seed), L.u64(salt), vptr(step_dev), stream())
+        ctx.meta = (seed, salt)
+        ctx.step_dev = step_dev
         return y
 
     @staticmethod
     def backward(ctx, dy):
         dy = _c(dy)
         dx = torch.empty_like(dy)
-        call("nemar_dropout", view(dy), view(dx), L.u64(ctx.meta[0]), L.u64(ctx.meta[1]), stream())
-        return dx, None, None
+        call("nemar_dropout_dev", view(dy), view(dx), L.u64(ctx.meta[0]), L.u64(ctx.meta[1]), vptr(ctx.step_dev), stream())
+        return dx, None, None, None
+
+
+def begin_step(device):
+    """Start of one optimize_parameters: advance the device step counter (a 1-thread kernel, captured with the step)
+    and restart the per-step numbering of the dropout call sites."""
+    from .config import CONFIG, step_counter
+    c = step_counter(device)
+    call("nemar_counter_add", vptr(c), i64(1), stream())
+    CONFIG.dropout_calls = 0
+    ARENA.begin(device)
+
+
+def end_step():
+    ARENA.end()
 
 
 # ------------------------------------------------------------------------------------------------
@@ -620,7 +753,7 @@ class SmoothnessFn(Function):
     def forward(ctx, off, img, alpha, scale):
         off = _c(off)
         n, h, w, cs = off.shape
-        loss = torch.zeros(1, dtype=torch.float32, device=off.device)
+        loss = ARENA.zeros((1,), off.device)
         use_img = img is not None and alpha > 0.0
         if use_img:
             img = _c(img)
@@ -652,7 +785,7 @@ class L1Fn(Function):
     @staticmethod
     def forward(ctx, a, b, scale):
         a, b = _c(a), _c(b)
-        out = torch.zeros(1, dtype=torch.float32, device=a.device)
+        out = ARENA.zeros((1,), a.device)
         call("nemar_l1_fwd", fptr(a), fptr(b), i64(a.numel()), float(scale), fptr(out), stream())
         ctx.save_for_backward(a, b)
         ctx.scale = scale
@@ -671,7 +804,7 @@ class MeanAbsFn(Function):
     @staticmethod
     def forward(ctx, a, scale):
         a = _c(a)
-        out = torch.zeros(1, dtype=torch.float32, device=a.device)
+        out = ARENA.zeros((1,), a.device)
         call("nemar_mean_abs_fwd", fptr(a), i64(a.numel()), float(scale), fptr(out), stream())
         ctx.save_for_backward(a)
         ctx.scale = scale
@@ -693,7 +826,7 @@ class MSEConstFn(Function):
     def forward(ctx, pred, target, scale, c=None):
         pred = _c(pred)
         c = pred.shape[3] if c is None else c       # real channels (the head may pad its output with zeros)
-        out = torch.zeros(1, dtype=torch.float32, device=pred.device)
+        out = ARENA.zeros((1,), pred.device)
         call("nemar_mse_const_fwd", view(pred, 0, 0, c), float(target), float(scale), fptr(out), stream())
         ctx.save_for_backward(pred)
         ctx.meta = (target, scale, c)
@@ -721,7 +854,7 @@ class MSEConstGroupsFn(Function):
         n = pred.shape[0] // k
         assert n * k == pred.shape[0]
         c = pred.shape[3] if c is None else c
-        out = torch.zeros(k, dtype=torch.float32, device=pred.device)
+        out = ARENA.zeros((k,), pred.device)
         for j, t in enumerate(targets):
             call("nemar_mse_const_fwd", view(pred[j * n:(j + 1) * n], 0, 0, c), float(t), float(scale), fptr(out[j:j + 1]), stream())
         ctx.save_for_backward(pred)

@@ -54,7 +54,7 @@ class FlatAdam:
         # the step number lives in device memory so that a captured step replays with the right bias correction
         F.adam_step_dev(self.flat_p, self.flat_g, self.exp_avg, self.exp_avg_sq, lr, self.betas[0], self.betas[1],
                         self.eps, self.step_dev, grad_scale)
-        F.bump_weights_epoch()
+        F.refresh_packs(self.flat_p)      # ONE launch re-packs the bf16 operand layouts of every layer just updated
 
     def state_dict(self):
         return {"step": self.step_count, "exp_avg": self.exp_avg.detach().cpu().clone(),

@@ -230,10 +230,6 @@ class NEMARModel(BaseModel):
 
     def _optimize_parameters_graphed(self):
         st = self.__dict__.setdefault("_graph_state", {"eager_steps": 0, "graph": None, "failed": False})
-        if not st["failed"] and not getattr(self.opt, "no_dropout", True):
-            # dropout draws its mask from a host-side (seed, offset) counter: a replay would repeat the captured mask
-            print("--cuda_graph 1 needs --no_dropout (a replay would repeat one dropout mask); continuing with eager launches")
-            st["failed"] = True
         if st["failed"]:
             return self._optimize_parameters_eager()
         lrs = (self.optimizer_TR.param_groups[0]["lr"], self.optimizer_D.param_groups[0]["lr"])
@@ -288,6 +284,8 @@ class NEMARModel(BaseModel):
             return self._optimize_parameters_eager()
 
     def _optimize_parameters_eager(self):
+        if self.device.type == "cuda":
+            F.begin_step(self.device)          # device step counter: dropout masks change per step, also under replay
         self.forward()
         # D phase
         self.set_requires_grad([self.netT, self.netR], False)
@@ -301,3 +299,4 @@ class NEMARModel(BaseModel):
         self.backward_T_and_R()
         self.optimizer_TR.step()          # all-reduce of the T+R bucket + flat Adam
         self.set_requires_grad([self.netD, *self.netD_multiresolution], True)
+        F.end_step()

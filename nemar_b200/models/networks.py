@@ -69,7 +69,8 @@ class Conv(nn.Module):
                             defer_bias_grad and bias is not None)
             ent = (cfg, self._packed if tag == "direct" else F.PackedWeights())
             self._cfgs[key] = ent
-        return F.Conv2dFn.apply(x, weight, bias, ent[0], ent[1])
+        # tap-transformed weights are temporaries derived from self.weight: their packs are keyed on the parameter
+        return F.Conv2dFn.apply(x, weight, bias, ent[0], ent[1], None if tag == "direct" else self.weight)
 
     # ---- k x k convolutions with <= 4 input or output channels as 1x1 tensor-core convolutions ------------------
     def taps_supported(self, x_dtype):
@@ -127,7 +128,6 @@ class ResnetBlock(nn.Module):
         self.second = "6" if use_dropout else "5"
         self.conv_block.add_module(self.second, Conv(dim, dim, 3, 1, 1, bias=use_bias))
         self.use_dropout = use_dropout
-        self._drop_calls = 0
 
     def run(self, t_padded, out_pad):
         """t_padded carries a reflect halo of 1 (it is both the conv input and the skip)."""
@@ -135,8 +135,11 @@ class ResnetBlock(nn.Module):
         c2 = getattr(self.conv_block, self.second)
         if self.use_dropout and self.training:
             u = conv_in_act(c1, t_padded, 1, L.ACT_RELU, out_pad=0)
-            self._drop_calls += 1
-            u = F.DropoutFn.apply(u, CONFIG.dropout_seed + id(self) % 65521, self._drop_calls * u.numel())
+            # salt: the n-th dropout site of this step (netT runs twice per step: two masks per block), spaced so that
+            # the per-element counters of two sites never overlap
+            from ..engine.config import step_counter
+            CONFIG.dropout_calls += 1
+            u = F.DropoutFn.apply(u, CONFIG.dropout_seed, CONFIG.dropout_calls << 40, step_counter(u.device))
             u = norm_act(u, None, L.ACT_NONE, None, 0, 1)
         else:
             u = conv_in_act(c1, t_padded, 1, L.ACT_RELU, out_pad=1)

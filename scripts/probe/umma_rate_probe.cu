@@ -20,7 +20,10 @@
 
 using namespace tc;
 
-template <int N>
+// ELECT = true: the issuing warp stays converged and one lane is chosen by elect.sync per group of 4 MMAs (what the
+// engine does since this probe); false: everything inside `threadIdx.x == 0` (what it did before: ptxas then wraps every
+// UTCHMMA in an ELECT / R2UR.BROADCAST / BRA.U.ANY waterfall loop).
+template <int N, bool ELECT>
 __global__ void __launch_bounds__(128) rate_kernel(int reps, int naccs, int kper, long long* cycles) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -37,7 +40,33 @@ __global__ void __launch_bounds__(128) rate_kernel(int reps, int naccs, int kper
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
-  if (threadIdx.x == 0) {
+  if (ELECT && warp == 0) {
+    constexpr uint32_t idesc = make_idesc_bf16(128, N, 0, 0);
+    const uint64_t adesc = make_smem_desc(smem_u32(sA), 16, 1024, LAYOUT_SW128);
+    const uint64_t bdesc = make_smem_desc(smem_u32(sB), 16, 1024, LAYOUT_SW128);
+    if (elect_one()) {
+      for (int k = 0; k < 4; ++k) umma_bf16(tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, k > 0);
+      umma_commit(bar);
+    }
+    __syncwarp();
+    mbar_wait(bar, 0);
+    tc_fence_after();
+    const long long t0 = clock64();
+    for (int r = 0; r < reps; r += 4) {
+      const uint32_t acc = tmem + (uint32_t)((r / kper) % naccs) * (uint32_t)N;
+      if (elect_one()) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_bf16(acc, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, 1u);
+      }
+      __syncwarp();
+    }
+    if (elect_one()) umma_commit(bar);
+    __syncwarp();
+    mbar_wait(bar, 1);
+    const long long t1 = clock64();
+    if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
+  }
+  if (!ELECT && threadIdx.x == 0) {
     constexpr uint32_t idesc = make_idesc_bf16(128, N, 0, 0);
     const uint64_t adesc = make_smem_desc(smem_u32(sA), 16, 1024, LAYOUT_SW128);
     const uint64_t bdesc = make_smem_desc(smem_u32(sB), 16, 1024, LAYOUT_SW128);
@@ -62,11 +91,11 @@ __global__ void __launch_bounds__(128) rate_kernel(int reps, int naccs, int kper
   if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem, 256); }
 }
 
-template <int N>
+template <int N, bool ELECT>
 static void run(int grid, int reps, int naccs, int kper, long long* d_cyc) {
   if (naccs * N > 256) return;
-  cudaFuncSetAttribute(rate_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-  rate_kernel<N><<<grid, 128, 56 * 1024>>>(reps, naccs, kper, d_cyc);
+  cudaFuncSetAttribute(rate_kernel<N, ELECT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+  rate_kernel<N, ELECT><<<grid, 128, 56 * 1024>>>(reps, naccs, kper, d_cyc);
   cudaError_t e = cudaDeviceSynchronize();
   if (e != cudaSuccess) { printf("N=%d naccs=%d: %s\n", N, naccs, cudaGetErrorString(e)); exit(1); }
   std::vector<long long> h(grid);
@@ -75,7 +104,7 @@ static void run(int grid, int reps, int naccs, int kper, long long* d_cyc) {
   for (long long v : h) { avg += (double)v; if ((double)v > mx) mx = (double)v; }
   avg /= grid;
   const double work = 128.0 * N * 16 / 4096.0;     // clk per MMA at 4096 MAC/clk/SM
-  printf("RATE N=%3d ctas/SM=%d accs=%d kper=%d : %7.1f clk/MMA (max %7.1f)  work %5.1f clk  -> %5.1f %% of the MMA rate per CTA\n", N,
+  printf("RATE %s N=%3d ctas/SM=%d accs=%d kper=%d : %7.1f clk/MMA (max %7.1f)  work %5.1f clk  -> %5.1f %% of the MMA rate per CTA\n", ELECT ? "elect " : "lane==0", N,
          grid > 148 ? 2 : 1, naccs, kper, avg / reps, mx / reps, work, 100.0 * work / (avg / reps));
 }
 
@@ -83,15 +112,19 @@ int main() {
   long long* d_cyc;
   cudaMalloc(&d_cyc, sizeof(long long) * 296);
   const int reps = 2048;
-  for (int grid : {148, 296})
-    for (int kper : {1, 4})
-      for (int naccs : {1, 2, 4, 8}) {
-        if (kper == 4 && naccs == 1) continue;
-        run<32>(grid, reps, naccs, kper, d_cyc);
-        run<64>(grid, reps, naccs, kper, d_cyc);
-        run<128>(grid, reps, naccs, kper, d_cyc);
-        run<256>(grid, reps, naccs, kper, d_cyc);
-      }
+  for (int grid : {148, 296}) {
+    for (int naccs : {1, 2}) {
+      run<32, false>(grid, reps, naccs, 4, d_cyc);
+      run<128, false>(grid, reps, naccs, 4, d_cyc);
+      run<256, false>(grid, reps, naccs, 4, d_cyc);
+    }
+    for (int naccs : {1, 2, 4}) {
+      run<32, true>(grid, reps, naccs, 4, d_cyc);
+      run<64, true>(grid, reps, naccs, 4, d_cyc);
+      run<128, true>(grid, reps, naccs, 4, d_cyc);
+      run<256, true>(grid, reps, naccs, 4, d_cyc);
+    }
+  }
   printf("SUMMARY done\n");
   return 0;
 }

@@ -86,6 +86,7 @@ def main():
             print("rank %d: %s replicas drifted by %.3e after %d steps" % (rank, name, drift, WARM_STEPS))
         ok = ok and drift == 0.0
     p0 = {name: o.flat_p.detach().clone() for name, o in (("TR", dp.optimizer_TR), ("D", dp.optimizer_D))}
+    opt0 = {name: o.state_dict() for name, o in (("TR", dp.optimizer_TR), ("D", dp.optimizer_D))}
     # 3. same step, N ranks vs one process
     g_dp = step_and_capture(dp, a, b)
     calls = dp.allreduce.calls
@@ -96,6 +97,9 @@ def main():
         single.optimizer_D.grad_hook = lambda flat: 1.0
         single.optimizer_TR.flat_p.copy_(p0["TR"])
         single.optimizer_D.flat_p.copy_(p0["D"])
+        # the T/R phase differentiates through the discriminator AFTER its Adam update: same moments, same step number
+        single.optimizer_TR.load_state_dict(opt0["TR"])
+        single.optimizer_D.load_state_dict(opt0["D"])
         F.bump_weights_epoch()
         g_1 = step_and_capture(single, A, B)
         for k in ("TR", "D"):

@@ -192,16 +192,18 @@ def test_cuda_graph_mode_state_machine(monkeypatch):
     m.set_input(batch(7))
     m._optimize_parameters_graphed()
     assert len(FakeGraph.made) == 2 and FakeGraph.made[1].replays == 1 and len(calls) == 6
-    # with dropout the step is never captured (a replay would repeat one mask)
+    # dropout does not prevent the capture: its masks are keyed by a device-resident step counter
     m2 = object.__new__(NM.NEMARModel)
     m2.opt = types.SimpleNamespace(cuda_graph=1, direction="AtoB", no_dropout=False)
     m2.device = torch.device("cpu")
+    m2.optimizer_TR = types.SimpleNamespace(param_groups=groups)
+    m2.optimizer_D = types.SimpleNamespace(param_groups=groups)
     ran = []
     m2._optimize_parameters_eager = lambda: ran.append(1)
     for k in range(6):
         m2.set_input(batch(k))
         m2._optimize_parameters_graphed()
-    assert len(ran) == 6 and len(FakeGraph.made) == 2
+    assert len(ran) == 4 and len(FakeGraph.made) == 3 and FakeGraph.made[2].replays == 3
 
 
 def test_reference_written_checkpoint_loads():

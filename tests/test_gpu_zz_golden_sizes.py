@@ -37,4 +37,5 @@ def test_first_step_images_fp32_vs_reference_golden_sizes(name):
     stride = int(g["img_stride"])
     for k in ("fake_B", "registered_real_A", "fake_TR_B", "fake_RT_B"):
         got = getattr(model, k).detach().cpu().numpy()[:, :, ::stride, ::stride]
-        np.testing.assert_allclose(got, g["img_" + k], rtol=0, atol=5e-4, err_msg=k)
+        # 1024^2: fake_TR_B = T(warp(A)) composes the 1M-point sampling grid (5e-5) with the generator: stated 1e-3
+        np.testing.assert_allclose(got, g["img_" + k], rtol=0, atol=1e-3 if name == "c5_1024" else 5e-4, err_msg=k)
