@@ -84,6 +84,11 @@ int nemar_cast_view(const nemar_tensor* src, const nemar_tensor* dst, void* stre
  *   gather_taps: dst[n,y,x,(a*k+b)*c+ch] = src[n, y+sgn*a, x+sgn*b, ch]   (ch < c; channels >= k*k*c are zeroed)
  *   sum_taps:    dst[n,y,x,ch] = act(bias[ch] + sum_{a,b} src[n, y-sgn*a, x-sgn*b, (a*k+b)*c+ch])   (ch < c) */
 int nemar_gather_taps(const nemar_tensor* src, const nemar_tensor* dst, int k, int c, int sgn, void* stream);
+/* rectangular tap window ky x kx (a < ky rows, b < kx columns; channel index (a*kx+b)*c+ch); (1, 7) is the column half
+ * of the generator's k7 head / tail, whose row half runs as a 7 x 1 tensor-core convolution */
+int nemar_gather_taps2(const nemar_tensor* src, const nemar_tensor* dst, int ky, int kx, int c, int sgn, void* stream);
+int nemar_sum_taps2(const nemar_tensor* src, const nemar_tensor* dst, int ky, int kx, int c, int sgn, const float* bias,
+                    int act, void* stream);
 int nemar_sum_taps(const nemar_tensor* src, const nemar_tensor* dst, int k, int c, int sgn, const float* bias,
                    int act, void* stream);
 /* dst view (=|+=) src view folded (adjoint of nemar_copy_view) */

@@ -11,8 +11,9 @@
 #include "conv_internal.cuh"
 
 static bool geom_ok(const nemar_conv_geom* g) {
+  // rectangular kernels (the 7 x 1 halves of the generator's k7 head / tail) only as "valid" stride-1 convolutions
   return g && g->cin > 0 && g->cout > 0 && g->kh > 0 && g->kw > 0 && g->stride > 0 && g->pad >= 0 &&
-         g->kh == g->kw;
+         (g->kh == g->kw || (g->pad == 0 && g->stride == 1 && !g->transposed));
 }
 
 NEMAR_API int nemar_pack_weights(const float* w, const nemar_conv_geom* g, int dtype, int cin_p, int cout_p,
@@ -37,8 +38,8 @@ NEMAR_API int nemar_pack_weights_multi(const nemar_pack_job* jobs_dev, const int
   return generic_pack_multi(jobs_dev, blocks_dev, nblocks, (cudaStream_t)stream);
 }
 
-static int expected_out(int in, const nemar_conv_geom* g) {
-  return (in + 2 * g->pad - g->kh) / g->stride + 1;
+static int expected_out(int in, const nemar_conv_geom* g, int k) {
+  return (in + 2 * g->pad - k) / g->stride + 1;
 }
 
 NEMAR_API int nemar_conv2d_fprop(const nemar_tensor* x, const void* w_packed, int w_cin_p, const float* bias,
@@ -55,14 +56,14 @@ NEMAR_API int nemar_conv2d_fprop(const nemar_tensor* x, const void* w_packed, in
   gg.kh = g->kh; gg.kw = g->kw; gg.dst_padded = 0;
   if (!g->transposed) {
     NEMAR_REQUIRE(x->pad <= g->pad, "conv2d_fprop: input halo larger than the conv padding");
-    NEMAR_REQUIRE(y->h == expected_out(x->h, g) && y->w == expected_out(x->w, g), "conv2d_fprop: bad output extent");
-    gg.sm = g->stride; gg.sd = 1; gg.pe = g->pad - x->pad;
+    NEMAR_REQUIRE(y->h == expected_out(x->h, g, g->kh) && y->w == expected_out(x->w, g, g->kw), "conv2d_fprop: bad output extent");
+    gg.sm = g->stride; gg.sd = 1; gg.pe = gg.pe_x = g->pad - x->pad;
   } else {
     NEMAR_REQUIRE(x->pad == 0, "conv2d_fprop(transposed): input halo not supported");
     int lo_h = (x->h - 1) * g->stride - 2 * g->pad + g->kh, lo_w = (x->w - 1) * g->stride - 2 * g->pad + g->kw;
     NEMAR_REQUIRE(y->h >= lo_h && y->h < lo_h + g->stride && y->w >= lo_w && y->w < lo_w + g->stride,
                   "conv2d_fprop(transposed): bad output extent");
-    gg.sm = 1; gg.sd = g->stride; gg.pe = g->kh - 1 - g->pad;
+    gg.sm = 1; gg.sd = g->stride; gg.pe = gg.pe_x = g->kh - 1 - g->pad;
   }
   if (use_tc && tc_gather_supported(x, y, w_cin_p, gg))   // otherwise: CUDA-core engine (still on the GPU)
     return tc_gather_gemm(x, y, w_packed, w_cin_p, bias, act, stats, gg, s);
@@ -85,10 +86,11 @@ NEMAR_API int nemar_conv2d_dgrad(const nemar_tensor* dy, const void* w_packed_d,
   gg.kh = g->kh; gg.kw = g->kw;
   if (!g->transposed) {
     NEMAR_REQUIRE(dx->pad <= g->pad, "conv2d_dgrad: dx halo larger than the conv padding");
-    gg.sm = 1; gg.sd = g->stride; gg.pe = g->kh - 1 - (g->pad - dx->pad); gg.dst_padded = dx->pad > 0;
+    gg.sm = 1; gg.sd = g->stride; gg.dst_padded = dx->pad > 0;
+    gg.pe = g->kh - 1 - (g->pad - dx->pad); gg.pe_x = g->kw - 1 - (g->pad - dx->pad);
   } else {
     NEMAR_REQUIRE(dx->pad == 0, "conv2d_dgrad(transposed): halo not supported");
-    gg.sm = g->stride; gg.sd = 1; gg.pe = g->pad; gg.dst_padded = 0;
+    gg.sm = g->stride; gg.sd = 1; gg.pe = gg.pe_x = g->pad; gg.dst_padded = 0;
   }
   if (use_tc && tc_gather_supported(dy, dx, w_cout_p, gg))
     return tc_gather_gemm(dy, dx, w_packed_d, w_cout_p, nullptr, NEMAR_ACT_NONE, nullptr, gg, s);

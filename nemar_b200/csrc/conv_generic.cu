@@ -42,7 +42,7 @@ gather_gemm_kernel(TView src, TView dst, const void* __restrict__ wp, int w_dtyp
       int y = (int)(r % DH);
       pn[tid] = (int)(r / DH);
       py[tid] = y * gg.sm - gg.pe;
-      px[tid] = x * gg.sm - gg.pe;
+      px[tid] = x * gg.sm - gg.pe_x;
     } else {
       pn[tid] = -1; py[tid] = 0; px[tid] = 0;
     }

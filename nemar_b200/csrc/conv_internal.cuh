@@ -21,7 +21,8 @@ struct GatherGeom {
   int kh, kw;
   int sm;          // multiplier applied to the destination coordinate
   int sd;          // divisor applied to the gathered coordinate (stride of a data-gradient pass)
-  int pe;          // effective padding: coordinate = dst*sm - pe + tap
+  int pe;          // effective padding (rows): coordinate = dst*sm - pe + tap
+  int pe_x;        // effective padding (columns); differs from pe only for rectangular kernels
   int dst_padded;  // 1: iterate over the destination's padded index space (gradient into a halo'd buffer)
 };
 

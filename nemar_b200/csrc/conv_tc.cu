@@ -928,9 +928,9 @@ int tc_gather_gemm(const nemar_tensor* src_in, const nemar_tensor* dst_in, const
     P.ntaps = 0;
     for (int a = 0; a < gg.kh; ++a)
       for (int b = 0; b < gg.kw; ++b) {
-        int oy = -gg.pe + a, ox = -gg.pe + b;   // source offset relative to dst*sm
+        int oy = -gg.pe + a, ox = -gg.pe_x + b;   // source offset relative to dst*sm
         if (gg.sd == 2) {
-          int uy = pyc - gg.pe + a, ux = pxc - gg.pe + b;
+          int uy = pyc - gg.pe + a, ux = pxc - gg.pe_x + b;
           if ((uy & 1) || (ux & 1)) continue;
           oy = uy >> 1; ox = ux >> 1;           // arithmetic shift == floor division (numerators are even)
         }

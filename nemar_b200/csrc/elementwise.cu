@@ -213,12 +213,12 @@ NEMAR_API int nemar_cast_view(const nemar_tensor* src, const nemar_tensor* dst, 
 }
 
 // ---- tap <-> channel transforms (k7 head / tail as 1x1 tensor-core convolutions) ----------------
-template <int KK, int CC>
-__global__ void gather_taps_kernel(TView s, TView d, int k_rt, int c_rt, int sgn) {
-  const int k = KK > 0 ? KK : k_rt, c = CC > 0 ? CC : c_rt;
+template <int KY, int KK, int CC>
+__global__ void gather_taps_kernel(TView s, TView d, int ky_rt, int k_rt, int c_rt, int sgn) {
+  const int k = KK > 0 ? KK : k_rt, c = CC > 0 ? CC : c_rt, ky = KY > 0 ? KY : ky_rt;   // ky x k taps
   // one thread -> 8 consecutive destination channels of one pixel (one 16-byte store when d is bf16)
   const uint32_t groups = d.c / 8;
-  const int kc = k * k * c;
+  const int kc = ky * k * c;
   const uint32_t total = (uint32_t)d.n * d.h * d.w * groups;      // < 2^32 for every size on the path
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     uint32_t r = i / groups;
@@ -253,9 +253,9 @@ __global__ void gather_taps_kernel(TView s, TView d, int k_rt, int c_rt, int sgn
   }
 }
 
-template <int KK, int CC>
-__global__ void sum_taps_kernel(TView s, TView d, int k_rt, int c_rt, int sgn, const float* __restrict__ bias, int act) {
-  const int k = KK > 0 ? KK : k_rt, c = CC > 0 ? CC : c_rt;
+template <int KY, int KK, int CC>
+__global__ void sum_taps_kernel(TView s, TView d, int ky_rt, int k_rt, int c_rt, int sgn, const float* __restrict__ bias, int act) {
+  const int k = KK > 0 ? KK : k_rt, c = CC > 0 ? CC : c_rt, ky = KY > 0 ? KY : ky_rt;
   const int64_t total = (int64_t)d.n * d.h * d.w;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     int x = (int)(i % d.w);
@@ -263,7 +263,7 @@ __global__ void sum_taps_kernel(TView s, TView d, int k_rt, int c_rt, int sgn, c
     int y = (int)(r % d.h);
     int nn = (int)(r / d.h);
     float acc[4] = {0.f, 0.f, 0.f, 0.f};     // c <= 4
-    for (int a = 0; a < k; ++a) {
+    for (int a = 0; a < ky; ++a) {
       int sy = y - sgn * a;
       if (sy < 0 || sy >= s.h) continue;
       for (int b = 0; b < k; ++b) {
@@ -282,29 +282,40 @@ __global__ void sum_taps_kernel(TView s, TView d, int k_rt, int c_rt, int sgn, c
   }
 }
 
-NEMAR_API int nemar_gather_taps(const nemar_tensor* src, const nemar_tensor* dst, int k, int c, int sgn, void* stream) {
+NEMAR_API int nemar_gather_taps2(const nemar_tensor* src, const nemar_tensor* dst, int ky, int kx, int c, int sgn, void* stream) {
   NEMAR_REQUIRE(view_ok(src) && view_ok(dst) && src->pad == 0 && dst->pad == 0 && src->n == dst->n, "gather_taps: bad views");
-  NEMAR_REQUIRE(k > 0 && c > 0 && c <= src->c && dst->c % 8 == 0 && dst->c >= k * k * c && (sgn == 1 || sgn == -1) &&
+  NEMAR_REQUIRE(ky > 0 && kx > 0 && c > 0 && c <= src->c && dst->c % 8 == 0 && dst->c >= ky * kx * c && (sgn == 1 || sgn == -1) &&
                     (dst->dtype != NEMAR_BF16 || ((dst->cs % 8 == 0) && (dst->coff % 8 == 0) && ((((uintptr_t)dst->ptr) & 15) == 0))),
                 "gather_taps: bad arguments");
   TView s = make_view(src), d = make_view(dst);
   int64_t total = (int64_t)d.n * d.h * d.w * (d.c / 8);
-  if (k == 7 && c == 3) gather_taps_kernel<7, 3><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(s, d, k, c, sgn);
-  else gather_taps_kernel<0, 0><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(s, d, k, c, sgn);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (ky == 7 && kx == 7 && c == 3) gather_taps_kernel<7, 7, 3><<<grid_for(total, 256), 256, 0, st>>>(s, d, ky, kx, c, sgn);
+  else if (ky == 1 && kx == 7 && c == 3) gather_taps_kernel<1, 7, 3><<<grid_for(total, 256), 256, 0, st>>>(s, d, ky, kx, c, sgn);
+  else gather_taps_kernel<0, 0, 0><<<grid_for(total, 256), 256, 0, st>>>(s, d, ky, kx, c, sgn);
   NEMAR_LAUNCH_CHECK();
   return 0;
 }
+NEMAR_API int nemar_gather_taps(const nemar_tensor* src, const nemar_tensor* dst, int k, int c, int sgn, void* stream) {
+  return nemar_gather_taps2(src, dst, k, k, c, sgn, stream);
+}
 
-NEMAR_API int nemar_sum_taps(const nemar_tensor* src, const nemar_tensor* dst, int k, int c, int sgn, const float* bias,
-                             int act, void* stream) {
+NEMAR_API int nemar_sum_taps2(const nemar_tensor* src, const nemar_tensor* dst, int ky, int kx, int c, int sgn, const float* bias,
+                              int act, void* stream) {
   NEMAR_REQUIRE(view_ok(src) && view_ok(dst) && src->pad == 0 && dst->pad == 0 && src->n == dst->n, "sum_taps: bad views");
-  NEMAR_REQUIRE(k > 0 && c > 0 && c <= 4 && c <= dst->c && src->c >= k * k * c && (sgn == 1 || sgn == -1), "sum_taps: bad arguments");
+  NEMAR_REQUIRE(ky > 0 && kx > 0 && c > 0 && c <= 4 && c <= dst->c && src->c >= ky * kx * c && (sgn == 1 || sgn == -1), "sum_taps: bad arguments");
   TView s = make_view(src), d = make_view(dst);
   int64_t total = (int64_t)d.n * d.h * d.w;
-  if (k == 7 && c == 3) sum_taps_kernel<7, 3><<<grid_for(total, 128), 128, 0, (cudaStream_t)stream>>>(s, d, k, c, sgn, bias, act);
-  else sum_taps_kernel<0, 0><<<grid_for(total, 128), 128, 0, (cudaStream_t)stream>>>(s, d, k, c, sgn, bias, act);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (ky == 7 && kx == 7 && c == 3) sum_taps_kernel<7, 7, 3><<<grid_for(total, 128), 128, 0, st>>>(s, d, ky, kx, c, sgn, bias, act);
+  else if (ky == 1 && kx == 7 && c == 3) sum_taps_kernel<1, 7, 3><<<grid_for(total, 128), 128, 0, st>>>(s, d, ky, kx, c, sgn, bias, act);
+  else sum_taps_kernel<0, 0, 0><<<grid_for(total, 128), 128, 0, st>>>(s, d, ky, kx, c, sgn, bias, act);
   NEMAR_LAUNCH_CHECK();
   return 0;
+}
+NEMAR_API int nemar_sum_taps(const nemar_tensor* src, const nemar_tensor* dst, int k, int c, int sgn, const float* bias,
+                             int act, void* stream) {
+  return nemar_sum_taps2(src, dst, k, k, c, sgn, bias, act, stream);
 }
 
 template <typename T, int V>

@@ -7,6 +7,10 @@ class EngineConfig:
         self.precision = "bf16"      # storage dtype of activations / packed weights: "bf16" | "fp32"
         self.conv_engine = "auto"    # "auto": tcgen05 where supported, else generic; "generic": CUDA cores only
         self.dropout_seed = 0x5EED
+        # k7 head / tail of the generator: column taps as channels + a 7 x 1 tensor-core conv (True), or all 49 taps as
+        # channels + a 1 x 1 conv (False: round 1's formulation, 5x the intermediate bytes)
+        import os
+        self.k7_xtaps = os.environ.get("NEMAR_K7_XTAPS", "1") != "0"
         self.step_dev = None         # device-resident step counter (int64[1]) read by the dropout kernels
         self.dropout_calls = 0       # dropout call sites seen since the step began (-> a distinct salt per site)
 

@@ -225,8 +225,11 @@ class ConvCfg:
 
     def __init__(self, cin, cout, k, stride=1, pad=0, transposed=False, x_pad=0, act=L.ACT_NONE, stats=False,
                  out_f32=False, out_pad_t=0, use_tc=False, cout_p=None, defer_bias_grad=False):
-        self.geom = L.ConvGeom(cin, cout, k, k, stride, pad, int(transposed))
-        self.cin, self.cout, self.k, self.stride, self.pad = cin, cout, k, stride, pad
+        # k: an int (square kernel) or (kh, kw) — rectangular kernels only as valid stride-1 convolutions
+        kh, kw = (k, k) if isinstance(k, int) else (int(k[0]), int(k[1]))
+        self.geom = L.ConvGeom(cin, cout, kh, kw, stride, pad, int(transposed))
+        self.kh, self.kw = kh, kw
+        self.cin, self.cout, self.k, self.stride, self.pad = cin, cout, kh, stride, pad
         self.transposed, self.x_pad, self.act, self.stats = transposed, x_pad, act, stats
         self.out_f32, self.out_pad_t, self.use_tc = out_f32, out_pad_t, use_tc
         self.cout_p = cout if cout_p is None else cout_p
@@ -235,10 +238,10 @@ class ConvCfg:
 
     def out_hw(self, h, w):
         if not self.transposed:
-            f = lambda v: (v + 2 * self.pad - self.k) // self.stride + 1
+            f = lambda v, k: (v + 2 * self.pad - k) // self.stride + 1
         else:
-            f = lambda v: (v - 1) * self.stride - 2 * self.pad + self.k + self.out_pad_t
-        return f(h), f(w)
+            f = lambda v, k: (v - 1) * self.stride - 2 * self.pad + k + self.out_pad_t
+        return f(h, self.kh), f(w, self.kw)
 
 
 class _PackJob(L.C.Structure):
@@ -276,7 +279,7 @@ class PackedWeights:
         ent = self.cache.get(key)
         stamp = self._stamp(weight, bias, owner)
         if ent is None:
-            k2 = cfg.k * cfg.k
+            k2 = cfg.kh * cfg.kw
             ent = {"wf": torch.empty(cfg.cout_p * k2 * cin_p, dtype=dtype, device=weight.device),
                    "wd": torch.empty(cin_p * k2 * cfg.cout_p, dtype=dtype, device=weight.device),
                    "bp": None, "stamp": None, "cfg": cfg, "cin_p": cin_p, "weight": None, "bias": None, "derived": owner is not None}
@@ -300,8 +303,8 @@ def _pack_jobs(ent):
     cfg, cin_p, w = ent["cfg"], ent["cin_p"], ent["weight"]
     code = L.dtype_code(ent["wf"])
     t = bool(cfg.transposed)
-    jobs = [_PackJob(w.data_ptr(), ent["wf"].data_ptr(), cfg.cout, cfg.cout_p, cfg.cin, cin_p, cfg.k, cfg.k, 0 if t else 1, 1 if t else 0, code, 1),
-            _PackJob(w.data_ptr(), ent["wd"].data_ptr(), cfg.cin, cin_p, cfg.cout, cfg.cout_p, cfg.k, cfg.k, 1 if t else 0, 0 if t else 1, code, 1)]
+    jobs = [_PackJob(w.data_ptr(), ent["wf"].data_ptr(), cfg.cout, cfg.cout_p, cfg.cin, cin_p, cfg.kh, cfg.kw, 0 if t else 1, 1 if t else 0, code, 1),
+            _PackJob(w.data_ptr(), ent["wd"].data_ptr(), cfg.cin, cin_p, cfg.cout, cfg.cout_p, cfg.kh, cfg.kw, 1 if t else 0, 0 if t else 1, code, 1)]
     if ent["bp"] is not None:
         jobs.append(_PackJob(ent["bias"].data_ptr(), ent["bp"].data_ptr(), cfg.cout, cfg.cout_p, 1, 1, 1, 1, 1, 0, L.F32, 2))
     return jobs
@@ -426,15 +429,25 @@ class TapsWeightFn(Function):
         ctx.param = weight
         if mode == "head":
             return weight.detach().permute(0, 2, 3, 1).reshape(co, k * k * ci, 1, 1).contiguous()
-        return weight.detach().permute(2, 3, 0, 1).reshape(k * k * co, ci, 1, 1).contiguous()
+        if mode == "tail":
+            return weight.detach().permute(2, 3, 0, 1).reshape(k * k * co, ci, 1, 1).contiguous()
+        # column taps folded into channels, row taps kept: a k x 1 convolution
+        if mode == "head_x":       # [co][ci][a][b] -> [co][(b,ci)][a][1]
+            return weight.detach().permute(0, 3, 1, 2).reshape(co, k * ci, k, 1).contiguous()
+        assert mode == "tail_x"    # [co][ci][a][b] -> [(b,co)][ci][a][1]
+        return weight.detach().permute(3, 0, 1, 2).reshape(k * co, ci, k, 1).contiguous()
 
     @staticmethod
     def backward(ctx, g):
         mode, co, ci, k = ctx.meta
         if mode == "head":
             gw = g.reshape(co, k, k, ci).permute(0, 3, 1, 2)
-        else:
+        elif mode == "tail":
             gw = g.reshape(k, k, co, ci).permute(2, 3, 0, 1)
+        elif mode == "head_x":
+            gw = g.reshape(co, k, ci, k).permute(0, 2, 3, 1)       # [co][b][ci][a] -> [co][ci][a][b]
+        else:
+            gw = g.reshape(k, co, ci, k).permute(1, 2, 3, 0)       # [b][co][ci][a] -> [co][ci][a][b]
         return _deliver(ctx.param, gw), None
 
 
@@ -443,21 +456,23 @@ class GatherTapsFn(Function):
     1x1 conv over k*k*c channels (generator head, networks.py:349-350)."""
 
     @staticmethod
-    def forward(ctx, x, k, c, sgn, oh, ow, cp, out_dtype):
+    def forward(ctx, x, k, c, sgn, oh, ow, cp, out_dtype, ky=None):
+        """ky: tap rows (default k: a square window); ky = 1 gathers the column taps only"""
         x = _c(x)
         n = x.shape[0]
+        ky = k if ky is None else ky
         out = torch.empty((n, oh, ow, cp), dtype=out_dtype, device=x.device)
-        call("nemar_gather_taps", view(x), view(out), k, c, sgn, stream())
-        ctx.meta = (k, c, sgn, x.shape, x.dtype)
+        call("nemar_gather_taps2", view(x), view(out), ky, k, c, sgn, stream())
+        ctx.meta = (ky, k, c, sgn, x.shape, x.dtype)
         return out
 
     @staticmethod
     def backward(ctx, g):
-        k, c, sgn, shape, dtype = ctx.meta
+        ky, k, c, sgn, shape, dtype = ctx.meta
         g = _c(g)
         dx = torch.empty(shape, dtype=dtype, device=g.device)
-        call("nemar_sum_taps", view(g), view(dx), k, c, sgn, None, L.ACT_NONE, stream())
-        return dx, None, None, None, None, None, None, None
+        call("nemar_sum_taps2", view(g), view(dx), ky, k, c, sgn, None, L.ACT_NONE, stream())
+        return dx, None, None, None, None, None, None, None, None
 
 
 class SumTapsFn(Function):
@@ -466,19 +481,20 @@ class SumTapsFn(Function):
     networks.py:375-377)."""
 
     @staticmethod
-    def forward(ctx, x, bias, k, c, sgn, oh, ow, cp, act):
+    def forward(ctx, x, bias, k, c, sgn, oh, ow, cp, act, ky=None):
         x = _c(x)
         n = x.shape[0]
+        ky = k if ky is None else ky
         y = torch.empty((n, oh, ow, cp), dtype=torch.float32, device=x.device)
-        call("nemar_sum_taps", view(x), view(y), k, c, sgn, fptr(bias.detach()) if bias is not None else None, act, stream())
-        ctx.meta = (k, c, sgn, x.shape, x.dtype, act, bias is not None)
+        call("nemar_sum_taps2", view(x), view(y), ky, k, c, sgn, fptr(bias.detach()) if bias is not None else None, act, stream())
+        ctx.meta = (ky, k, c, sgn, x.shape, x.dtype, act, bias is not None)
         ctx.bias_param = bias
         ctx.save_for_backward(y if act != L.ACT_NONE else None)
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        k, c, sgn, shape, dtype, act, has_bias = ctx.meta
+        ky, k, c, sgn, shape, dtype, act, has_bias = ctx.meta
         (y,) = ctx.saved_tensors
         dy = _c(dy)
         if act != L.ACT_NONE:
@@ -491,8 +507,8 @@ class SumTapsFn(Function):
             db = torch.empty(c, dtype=torch.float32, device=dy.device)
             call("nemar_bias_grad", view(g, 0, 0, c), fptr(db), stream())
         dx = torch.empty(shape, dtype=dtype, device=dy.device)
-        call("nemar_gather_taps", view(g), view(dx), k, c, sgn, stream())
-        return dx, _deliver(ctx.bias_param, db), None, None, None, None, None, None, None
+        call("nemar_gather_taps2", view(g), view(dx), ky, k, c, sgn, stream())
+        return dx, _deliver(ctx.bias_param, db), None, None, None, None, None, None, None, None
 
 
 # ------------------------------------------------------------------------------------------------

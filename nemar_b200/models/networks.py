@@ -26,7 +26,8 @@ def tc_policy(cin, cout, k, stride, transposed, dtype, cin_p):
     """Should this layer run on the tcgen05 engine?  (bf16 storage, input channels already a multiple of 16)"""
     if CONFIG.conv_engine != "auto" or dtype != torch.bfloat16 or cin_p % 16 != 0:
         return False
-    geom = L.ConvGeom(cin, cout, k, k, stride, 0, int(transposed))
+    kh, kw = (k, k) if isinstance(k, int) else k
+    geom = L.ConvGeom(cin, cout, kh, kw, stride, 0, int(transposed))
     return bool(L.lib().nemar_conv2d_tc_supported(L.C.byref(geom), L.BF16, 0, 0))
 
 
@@ -77,6 +78,28 @@ class Conv(nn.Module):
         cin, cout, k, stride, pad, transposed, _ = self.meta
         return (CONFIG.conv_engine == "auto" and x_dtype == torch.bfloat16 and not transposed and stride == 1 and k > 1 and
                 2 * pad == k - 1 and (cin <= 4 or cout <= 4))
+
+    def run_head_xtaps(self, x_padded, stats=True):
+        """cin <= 4, k x k on a halo'd input: the COLUMN taps are gathered into channels (k*cin of them: 21 for the
+        generator head instead of the 147 of a full tap gather, 64 B per pixel instead of 320), the ROW taps run as a
+        k x 1 tensor-core convolution whose TMA boxes shift by rows.  -> (y, stats) like run(stats=True)"""
+        cin, cout, k, _, pad, _, _ = self.meta
+        n, hp, wp, _ = x_padded.shape
+        kc = k * cin
+        u = F.GatherTapsFn.apply(x_padded, k, cin, 1, hp, wp - 2 * pad, (kc + 31) // 32 * 32, x_padded.dtype, 1)
+        w1 = F.TapsWeightFn.apply(self.weight, "head_x")                      # [co][(b,ci)][k][1]
+        return self._run(u, w1, self.bias, (kc, cout, (k, 1), 1, 0, False, 0), "head_xtaps", 0, L.ACT_NONE, stats, False, True)
+
+    def run_tail_xtaps(self, x_padded, act, cp=4):
+        """cout <= 4: a k x 1 convolution produces, per pixel of the row-valid / column-halo'd grid, the k*cout partial
+        sums of the column taps; the column-tap sum (+bias, act) completes the k x k convolution.
+        -> fp32 engine tensor [N,H,W,cp]"""
+        cin, cout, k, _, pad, _, _ = self.meta
+        n, hp, wp, _ = x_padded.shape
+        kc = k * cout
+        wv = F.TapsWeightFn.apply(self.weight, "tail_x")                      # [(b,co)][ci][k][1]
+        v = self._run(x_padded, wv, None, (cin, kc, (k, 1), 1, 0, False, 0), "tail_xtaps", 0, L.ACT_NONE, False, False, False)
+        return F.SumTapsFn.apply(v, self.bias, k, cout, -1, hp - 2 * pad, wp - 2 * pad, cp, act, 1)
 
     def run_head_taps(self, x_padded, stats=True):
         """cin <= 4: gather the k*k taps of the (halo'd) input into channels, then a 1x1 conv over k*k*cin channels.
@@ -170,7 +193,7 @@ class ResnetGenerator(nn.Module):
         g = lambda i: getattr(m, str(i))
         if g(1).taps_supported(CONFIG.dtype):
             t = F.ImagesToNHWC.apply(3, L.PAD_REFLECT, CONFIG.dtype, self.input_nc, x)
-            y, st = g(1).run_head_taps(t)
+            y, st = g(1).run_head_xtaps(t) if CONFIG.k7_xtaps else g(1).run_head_taps(t)
             t = norm_act(y, st, L.ACT_RELU, bias=g(1).bias)
         else:
             t = F.ImagesToNHWC.apply(3, L.PAD_REFLECT, CONFIG.dtype, image_channels(self.input_nc), x)
@@ -183,7 +206,7 @@ class ResnetGenerator(nn.Module):
         t = conv_in_act(g(b), t, 0, L.ACT_RELU)
         t = conv_in_act(g(b + 3), t, 0, L.ACT_RELU, out_pad=3)
         if g(b + 7).taps_supported(t.dtype):
-            y = g(b + 7).run_tail_taps(t, L.ACT_TANH)
+            y = g(b + 7).run_tail_xtaps(t, L.ACT_TANH) if CONFIG.k7_xtaps else g(b + 7).run_tail_taps(t, L.ACT_TANH)
         else:
             y = g(b + 7).run(t, x_pad=3, act=L.ACT_TANH, out_f32=True)
         return F.ToNCHW.apply(y, self.output_nc)

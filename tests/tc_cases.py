@@ -38,6 +38,9 @@ CASES = [
     (256, 256, 3, 1, 1, False, 1, 3, 8, 16, 0, False, "256->256 reflect, 3 destination tiles (pair tail)"),
     (256, 512, 3, 1, 1, False, 0, 2, 16, 16, L.ACT_LRELU, False, "256->512: two 256-channel destination tiles, two wgrad pairs"),
     (512, 256, 3, 1, 1, False, 0, 2, 16, 16, 0, False, "512->256: 8 k-chunks per tap, two 256-channel wgrad N tiles"),
+    # ---- rectangular 7 x 1 kernels: the row halves of the generator's k7 head / tail (column taps live in the channels)
+    (21, 64, (7, 1), 1, 0, False, 0, 2, 38, 32, 0, False, "k7 head as 7x1 over 21 column-tap channels (padded to 32)"),
+    (64, 21, (7, 1), 1, 0, False, 0, 2, 38, 38, 0, False, "k7 tail as 7x1 producing 21 column-tap partial sums"),
 ]
 
 # cases with a 256-multiple channel count on a tensor-core destination (fprop: cout, dgrad: cin) or in the wgrad
@@ -48,8 +51,9 @@ def _mk(case, seed=0):
     cin, cout, k, stride, pad, transposed, x_pad, n, h, w = case[:10]
     g = torch.Generator().manual_seed(seed)
     x = torch.randn((n, cin, h, w), generator=g)
-    wshape = (cin, cout, k, k) if transposed else (cout, cin, k, k)
-    wt = torch.randn(wshape, generator=g) * (cin * k * k) ** -0.5
+    kh, kw = (k, k) if isinstance(k, int) else k
+    wshape = (cin, cout, kh, kw) if transposed else (cout, cin, kh, kw)
+    wt = torch.randn(wshape, generator=g) * (cin * kh * kw) ** -0.5
     b = torch.randn(cout, generator=g) * 0.1
     return x, wt, b
 
@@ -119,4 +123,4 @@ def check(res):
 
 # stride-1 k x k geometries the resident-patch kernel (NEMAR_TC_RP3=1) takes: <= 64 output channels per tile, weight pack
 # and two patches within shared memory (fprop and/or dgrad side)
-RP3_CASES = [i for i, c in enumerate(CASES) if c[2] > 1 and c[3] == 1 and not c[5] and (c[0] <= 96 or c[1] <= 96)]
+RP3_CASES = [i for i, c in enumerate(CASES) if c[2] != 1 and c[3] == 1 and not c[5] and (c[0] <= 96 or c[1] <= 96)]

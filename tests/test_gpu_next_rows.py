@@ -103,7 +103,8 @@ def test_training_through_prefetcher_equals_direct_feed():
                 model.optimize_parameters()
                 losses.append(list(model.get_current_losses().values()))
         out[mode] = np.array(losses)
-    np.testing.assert_allclose(out["prefetch"][0], out["direct"][0], rtol=1e-5, atol=1e-6)
+    # same input bits => same step up to the atomics-ordered reductions (two direct runs differ by as much)
+    np.testing.assert_allclose(out["prefetch"][0], out["direct"][0], rtol=5e-4, atol=1e-5)
     np.testing.assert_allclose(out["prefetch"], out["direct"], rtol=0.3, atol=0.3)      # later steps: chaotic
 
 
