@@ -461,7 +461,13 @@ static int launch_plane_reduce(const nemar_tensor* xt, const float* stats, int a
   // forward 2.71 -> 2.82, backward apply 6.96 -> 7.32 — so only the backward reduction takes the fast path
   if ((nlean::enabled_mask() & (MODE == 0 ? 2 : 4)) && nfast::eligible(xt) && (!dyt || nfast::eligible(dyt))) {
     dim3 grid(nlean::chunks_for(hw, x.c / 8, x.n, true), x.n);
-    if (MODE == 0) {
+    if (nlean::reduce_u() == 4) {
+      if (MODE == 0) {
+        nlean::reduce_kernel<MODE, 4, NEMAR_ACT_NONE><<<grid, 256, sizeof(float) * 4 * x.c, s>>>(x, stats, act, dy, pad_mode, inv_hw, out);
+      } else {
+        NLEAN_ACT_SWITCH(act, (nlean::reduce_kernel<MODE, 4, A><<<grid, 256, sizeof(float) * 4 * x.c, s>>>(x, stats, act, dy, pad_mode, inv_hw, out)));
+      }
+    } else if (MODE == 0) {
       nlean::reduce_kernel<MODE, 2, NEMAR_ACT_NONE><<<grid, 256, sizeof(float) * 4 * x.c, s>>>(x, stats, act, dy, pad_mode, inv_hw, out);
     } else {
       NLEAN_ACT_SWITCH(act, (nlean::reduce_kernel<MODE, 2, A><<<grid, 256, sizeof(float) * 4 * x.c, s>>>(x, stats, act, dy, pad_mode, inv_hw, out)));
@@ -644,7 +650,11 @@ NEMAR_API int nemar_norm_act_fwd(const nemar_tensor* x, const float* stats, int 
   cudaStream_t s = (cudaStream_t)stream;
   if ((nlean::enabled_mask() & 1) && nfast::eligible(x) && nfast::eligible(y) && (!residual || nfast::eligible(residual))) {
     dim3 grid(nlean::chunks_for((int64_t)yv.hp * yv.wp, yv.c / 8, yv.n), yv.n);
-    NLEAN_ACT_SWITCH(act, (nlean::fwd_kernel<A><<<grid, 256, sizeof(float) * 2 * yv.c, s>>>(xv, stats, act, rv, residual != nullptr, yv, pad_mode, inv_hw)));
+    if (nlean::stream_u() == 4) {
+      NLEAN_ACT_SWITCH(act, (nlean::fwd_kernel<A, 4><<<grid, 256, sizeof(float) * 2 * yv.c, s>>>(xv, stats, act, rv, residual != nullptr, yv, pad_mode, inv_hw)));
+    } else {
+      NLEAN_ACT_SWITCH(act, (nlean::fwd_kernel<A, 2><<<grid, 256, sizeof(float) * 2 * yv.c, s>>>(xv, stats, act, rv, residual != nullptr, yv, pad_mode, inv_hw)));
+    }
     NEMAR_LAUNCH_CHECK();
     return 0;
   }
@@ -811,8 +821,13 @@ NEMAR_API int nemar_norm_act_bwd_apply(const nemar_tensor* x, const float* stats
   if ((nlean::enabled_mask() & 8) && nfast::eligible(x) && nfast::eligible(dy) && nfast::eligible(dx) && (!dres || nfast::eligible(dres))) {
     if (db && !db_accumulate) cudaMemsetAsync(db, 0, sizeof(float) * xv.c, s);
     dim3 grid(nlean::chunks_for((int64_t)xv.h * xv.w, xv.c / 8, xv.n, false, true), xv.n);
-    NLEAN_ACT_SWITCH(act, (nlean::bwd_apply_kernel<A><<<grid, 256, sizeof(float) * 5 * xv.c, s>>>(
-        xv, stats, act, dyv, pad_mode, red, dxv, dr, dres != nullptr, dres_accumulate, inv_hw, db)));
+    if (nlean::stream_u() == 4) {
+      NLEAN_ACT_SWITCH(act, (nlean::bwd_apply_kernel<A, 4><<<grid, 256, sizeof(float) * 5 * xv.c, s>>>(
+          xv, stats, act, dyv, pad_mode, red, dxv, dr, dres != nullptr, dres_accumulate, inv_hw, db)));
+    } else {
+      NLEAN_ACT_SWITCH(act, (nlean::bwd_apply_kernel<A, 2><<<grid, 256, sizeof(float) * 5 * xv.c, s>>>(
+          xv, stats, act, dyv, pad_mode, red, dxv, dr, dres != nullptr, dres_accumulate, inv_hw, db)));
+    }
     NEMAR_LAUNCH_CHECK();
     return 0;
   }

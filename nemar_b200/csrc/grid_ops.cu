@@ -145,12 +145,13 @@ struct Taps {
 
 __device__ __forceinline__ Taps make_taps(float gx, float gy, int w, int h) {
   Taps t;
-  // ATen grid_sampler_unnormalize, align_corners=False: ((coord + 1) * size - 1) / 2 — every operation rounded on its
-  // own (_rn intrinsics are never contracted): nvcc would otherwise fuse the multiply and the subtraction into one FMA,
-  // which moves ix by one ulp for sizes that are not powers of two (384, 288: found by the 288x384 index test) and with
-  // it, for samples that sit on a pixel boundary, the INTEGER tap index
-  t.ix = __fdiv_rn(__fsub_rn(__fmul_rn(__fadd_rn(gx, 1.f), (float)w), 1.f), 2.f);
-  t.iy = __fdiv_rn(__fsub_rn(__fmul_rn(__fadd_rn(gy, 1.f), (float)h), 1.f), 2.f);
+  // ATen grid_sampler_unnormalize, align_corners=False: ((coord + 1) * size - 1) / 2.  Both ATen builds evaluate the
+  // product and the subtraction as ONE fused multiply-add (the vectorised CPU kernel as fma(coord + 1, size / 2, -0.5),
+  // the CUDA kernel through nvcc's contraction) — measured: the fused form reproduces F.grid_sample on CPU to 1.2e-7 at
+  // 288 x 384, the two-rounding form only to 1.4e-5 (the forms coincide for power-of-two sizes).  Written as an
+  // explicit fma so that the INTEGER tap index does not depend on a compiler's contraction choices.
+  t.ix = __fmaf_rn(__fadd_rn(gx, 1.f), (float)w * 0.5f, -0.5f);
+  t.iy = __fmaf_rn(__fadd_rn(gy, 1.f), (float)h * 0.5f, -0.5f);
   float fx = floorf(t.ix), fy = floorf(t.iy);
   t.x0 = (int)fx;
   t.y0 = (int)fy;
@@ -337,290 +338,6 @@ grid_sample_fwd_shared_kernel(const float* __restrict__ img0, const float* __res
   }
 }
 
-// ---------------------------------------------------------------------------------------------
-// Shared-memory tiled variants (the default for C = 3).  One block = a 32 x 16 tile of output points, two horizontally
-// adjacent points per thread (128-bit grid loads).  The integer taps of the tile are reduced to a bounding box; when
-// it fits the staging window (48 x 32 input pixels: every near-identity deformation does) the window of each image
-// channel is copied into shared memory with coalesced row loads and the four taps of every point are gathered from
-// there; the backward pass accumulates the tile's scatter-add in a shared window as well and flushes every touched
-// input pixel with ONE global RED.  A tile whose taps do not fit (far-flung sampling) takes the direct per-point path
-// inside the same kernel.  Tap arithmetic (make_taps) and the nw, ne, sw, se accumulation order are those of the
-// direct kernels: identical indices and forward values.
-// ---------------------------------------------------------------------------------------------
-constexpr int GT_TW = 32, GT_TH = 16, GT_WX = 48, GT_WY = 32, GT_THREADS = 256;
-
-struct TileBox { int x0, y0, x1, y1, fits; };
-
-// bounding box of the in-range taps of the block's points (block-wide min / max through shared memory)
-__device__ __forceinline__ TileBox tile_box(const Taps (&t)[2], const bool (&act)[2], int w, int h, int* sred) {
-  int mnx = 1 << 30, mny = 1 << 30, mxx = -(1 << 30), mxy = -(1 << 30);
-#pragma unroll
-  for (int p = 0; p < 2; ++p) {
-    // a point whose four taps are all outside the image contributes nothing and does not widen the window
-    const bool live = act[p] && t[p].x0 >= -1 && t[p].x0 <= w - 1 && t[p].y0 >= -1 && t[p].y0 <= h - 1;
-    if (live) {
-      mnx = min(mnx, max(t[p].x0, 0)); mxx = max(mxx, min(t[p].x0 + 1, w - 1));
-      mny = min(mny, max(t[p].y0, 0)); mxy = max(mxy, min(t[p].y0 + 1, h - 1));
-    }
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    mnx = min(mnx, __shfl_xor_sync(0xffffffffu, mnx, o)); mny = min(mny, __shfl_xor_sync(0xffffffffu, mny, o));
-    mxx = max(mxx, __shfl_xor_sync(0xffffffffu, mxx, o)); mxy = max(mxy, __shfl_xor_sync(0xffffffffu, mxy, o));
-  }
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (lane == 0) { sred[warp * 4] = mnx; sred[warp * 4 + 1] = mny; sred[warp * 4 + 2] = mxx; sred[warp * 4 + 3] = mxy; }
-  __syncthreads();
-  TileBox b;
-  b.x0 = sred[0]; b.y0 = sred[1]; b.x1 = sred[2]; b.y1 = sred[3];
-#pragma unroll
-  for (int k = 1; k < GT_THREADS / 32; ++k) {
-    b.x0 = min(b.x0, sred[k * 4]); b.y0 = min(b.y0, sred[k * 4 + 1]);
-    b.x1 = max(b.x1, sred[k * 4 + 2]); b.y1 = max(b.y1, sred[k * 4 + 3]);
-  }
-  b.x0 &= ~3;                                    // 16-byte aligned window rows
-  b.fits = (b.x1 >= b.x0) && (b.x1 - b.x0 < GT_WX) && (b.y1 - b.y0 < GT_WY);
-  return b;
-}
-
-// copy rows [y0, y1] x columns [x0, x0 + GT_WX) of `planes` image planes into shared memory (zero beyond the image)
-__device__ __forceinline__ void stage_window(float* sw, const float* __restrict__ img, int planes, int h, int w, const TileBox& b) {
-  const int rows = b.y1 - b.y0 + 1;
-  const bool vec = (w & 3) == 0 && ((((uintptr_t)img) & 15) == 0);
-  const int items = planes * rows * (GT_WX / 4);
-  for (int i = threadIdx.x; i < items; i += GT_THREADS) {
-    const int q = i % (GT_WX / 4);
-    int r = i / (GT_WX / 4);
-    const int pl = r / rows;
-    r -= pl * rows;
-    const int x = b.x0 + q * 4;
-    const float* src = img + (size_t)pl * h * w + (size_t)(b.y0 + r) * w + x;
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (vec && x + 3 < w) v = __ldg(reinterpret_cast<const float4*>(src));
-    else {
-      if (x < w) v.x = __ldg(src);
-      if (x + 1 < w) v.y = __ldg(src + 1);
-      if (x + 2 < w) v.z = __ldg(src + 2);
-      if (x + 3 < w) v.w = __ldg(src + 3);
-    }
-    *reinterpret_cast<float4*>(sw + ((size_t)pl * GT_WY + r) * GT_WX + q * 4) = v;
-  }
-}
-
-template <int C, int NIMG>
-__global__ void __launch_bounds__(GT_THREADS)
-grid_sample_fwd_tiled_kernel(const float* __restrict__ img0, const float* __restrict__ img1, int n, int h, int w,
-                             const float* __restrict__ grid, int ho, int wo, float* __restrict__ out0,
-                             float* __restrict__ out1, int tiles_x, int tiles_y) {
-  extern __shared__ __align__(16) float gsm[];
-  float* swin = gsm;                                        // [NIMG][C][GT_WY][GT_WX]
-  int* sred = reinterpret_cast<int*>(gsm + NIMG * C * GT_WY * GT_WX);
-  int tb = blockIdx.x;
-  const int tx = tb % tiles_x; tb /= tiles_x;
-  const int ty = tb % tiles_y;
-  const int nn = tb / tiles_y;
-  const int px = tx * GT_TW + (threadIdx.x % (GT_TW / 2)) * 2, py = ty * GT_TH + threadIdx.x / (GT_TW / 2);
-  const size_t ihw = (size_t)h * w, ohw = (size_t)ho * wo;
-  const bool row_ok = py < ho;
-  bool act[2] = {row_ok && px < wo, row_ok && px + 1 < wo};
-  Taps t[2];
-  {
-    const float* gp = grid + ((size_t)nn * ohw + (size_t)py * wo + px) * 2;
-    float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (act[1] && ((((uintptr_t)gp) & 15) == 0)) g = __ldg(reinterpret_cast<const float4*>(gp));
-    else {
-      if (act[0]) { g.x = __ldg(gp); g.y = __ldg(gp + 1); }
-      if (act[1]) { g.z = __ldg(gp + 2); g.w = __ldg(gp + 3); }
-    }
-    t[0] = make_taps(g.x, g.y, w, h);
-    t[1] = make_taps(g.z, g.w, w, h);
-  }
-  const TileBox b = tile_box(t, act, w, h, sred);
-  if (b.fits) {
-    stage_window(swin, img0 + (size_t)nn * C * ihw, C, h, w, b);
-    if (NIMG == 2) stage_window(swin + C * GT_WY * GT_WX, img1 + (size_t)nn * C * ihw, C, h, w, b);
-  }
-  __syncthreads();
-#pragma unroll
-  for (int im = 0; im < NIMG; ++im) {
-    const float* img = (im == 0 ? img0 : img1) + (size_t)nn * C * ihw;
-    float* out = (im == 0 ? out0 : out1) + (size_t)nn * C * ohw + (size_t)py * wo + px;
-    const float* sw = swin + im * C * GT_WY * GT_WX;
-#pragma unroll
-    for (int ch = 0; ch < C; ++ch) {
-      float res[2];
-#pragma unroll
-      for (int p = 0; p < 2; ++p) {
-        const int x0 = t[p].x0, y0 = t[p].y0;
-        const bool xin0 = (x0 >= 0) & (x0 < w), xin1 = (x0 + 1 >= 0) & (x0 + 1 < w);
-        const bool yin0 = (y0 >= 0) & (y0 < h), yin1 = (y0 + 1 >= 0) & (y0 + 1 < h);
-        float vnw = 0.f, vne = 0.f, vsw = 0.f, vse = 0.f;
-        if (act[p]) {
-          if (b.fits) {
-            const float* s0 = sw + ((size_t)ch * GT_WY + (y0 - b.y0)) * GT_WX + (x0 - b.x0);
-            if (xin0 && yin0) vnw = s0[0];
-            if (xin1 && yin0) vne = s0[1];
-            if (xin0 && yin1) vsw = s0[GT_WX];
-            if (xin1 && yin1) vse = s0[GT_WX + 1];
-          } else {
-            const float* g0 = img + (size_t)ch * ihw + (ptrdiff_t)y0 * w + x0;
-            if (xin0 && yin0) vnw = __ldg(g0);
-            if (xin1 && yin0) vne = __ldg(g0 + 1);
-            if (xin0 && yin1) vsw = __ldg(g0 + w);
-            if (xin1 && yin1) vse = __ldg(g0 + w + 1);
-          }
-        }
-        float acc = vnw * t[p].nw;
-        acc += vne * t[p].ne;
-        acc += vsw * t[p].sw;
-        acc += vse * t[p].se;
-        res[p] = acc;
-      }
-      float* o = out + (size_t)ch * ohw;
-      if (act[1] && ((((uintptr_t)o) & 7) == 0)) *reinterpret_cast<float2*>(o) = make_float2(res[0], res[1]);
-      else {
-        if (act[0]) o[0] = res[0];
-        if (act[1]) o[1] = res[1];
-      }
-    }
-  }
-}
-
-// Backward, same tiling.  G0 / G1: does image 0 / 1 receive a gradient (real_A does not, fake_B does).
-template <int C, int NIMG, bool G0, bool G1>
-__global__ void __launch_bounds__(GT_THREADS)
-grid_sample_bwd_tiled_kernel(const float* __restrict__ img0, const float* __restrict__ img1, int n, int h, int w,
-                             const float* __restrict__ grid, int ho, int wo, const float* __restrict__ dout0,
-                             const float* __restrict__ dout1, float* __restrict__ dimg0, float* __restrict__ dimg1,
-                             float* __restrict__ dgrid, int tiles_x, int tiles_y) {
-  extern __shared__ __align__(16) float gsm[];
-  constexpr int WIN = C * GT_WY * GT_WX;
-  constexpr int NG = (G0 ? 1 : 0) + ((NIMG == 2 && G1) ? 1 : 0);
-  float* swin = gsm;                                        // image windows [NIMG][C][WY][WX]
-  float* sacc = gsm + NIMG * WIN;                           // gradient windows [NG][C][WY][WX]
-  int* sred = reinterpret_cast<int*>(sacc + NG * WIN);
-  int tb = blockIdx.x;
-  const int tx = tb % tiles_x; tb /= tiles_x;
-  const int ty = tb % tiles_y;
-  const int nn = tb / tiles_y;
-  const int px = tx * GT_TW + (threadIdx.x % (GT_TW / 2)) * 2, py = ty * GT_TH + threadIdx.x / (GT_TW / 2);
-  const size_t ihw = (size_t)h * w, ohw = (size_t)ho * wo;
-  const bool row_ok = py < ho;
-  bool act[2] = {row_ok && px < wo, row_ok && px + 1 < wo};
-  Taps t[2];
-  const size_t gidx = (size_t)nn * ohw + (size_t)py * wo + px;
-  {
-    const float* gp = grid + gidx * 2;
-    float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (act[1] && ((((uintptr_t)gp) & 15) == 0)) g = __ldg(reinterpret_cast<const float4*>(gp));
-    else {
-      if (act[0]) { g.x = __ldg(gp); g.y = __ldg(gp + 1); }
-      if (act[1]) { g.z = __ldg(gp + 2); g.w = __ldg(gp + 3); }
-    }
-    t[0] = make_taps(g.x, g.y, w, h);
-    t[1] = make_taps(g.z, g.w, w, h);
-  }
-  const TileBox b = tile_box(t, act, w, h, sred);
-  if (b.fits) {
-    stage_window(swin, img0 + (size_t)nn * C * ihw, C, h, w, b);
-    if (NIMG == 2) stage_window(swin + WIN, img1 + (size_t)nn * C * ihw, C, h, w, b);
-    for (int i = threadIdx.x; i < NG * WIN / 4; i += GT_THREADS) reinterpret_cast<float4*>(sacc)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-  }
-  __syncthreads();
-  float gix[2] = {0.f, 0.f}, giy[2] = {0.f, 0.f};
-#pragma unroll
-  for (int im = 0; im < NIMG; ++im) {
-    const bool wants = im == 0 ? G0 : G1;
-    const float* img = (im == 0 ? img0 : img1) + (size_t)nn * C * ihw;
-    const float* dout = (im == 0 ? dout0 : dout1) + (size_t)nn * C * ohw + (size_t)py * wo + px;
-    float* dimg = (im == 0 ? dimg0 : dimg1);
-    const float* sw = swin + im * WIN;
-    float* sa = sacc + ((im == 1 && G0) ? WIN : 0);
-#pragma unroll
-    for (int ch = 0; ch < C; ++ch) {
-      float go[2] = {0.f, 0.f};
-      {
-        const float* d = dout + (size_t)ch * ohw;
-        if (act[1] && ((((uintptr_t)d) & 7) == 0)) { const float2 v = __ldg(reinterpret_cast<const float2*>(d)); go[0] = v.x; go[1] = v.y; }
-        else { if (act[0]) go[0] = __ldg(d); if (act[1]) go[1] = __ldg(d + 1); }
-      }
-#pragma unroll
-      for (int p = 0; p < 2; ++p) {
-        if (!act[p]) continue;
-        const int x0 = t[p].x0, y0 = t[p].y0;
-        const bool xin0 = (x0 >= 0) & (x0 < w), xin1 = (x0 + 1 >= 0) & (x0 + 1 < w);
-        const bool yin0 = (y0 >= 0) & (y0 < h), yin1 = (y0 + 1 >= 0) & (y0 + 1 < h);
-        const float fx = (float)x0, fy = (float)y0, x1 = fx + 1.f, y1 = fy + 1.f;
-        float vnw = 0.f, vne = 0.f, vsw = 0.f, vse = 0.f;
-        const int so = (ch * GT_WY + (y0 - b.y0)) * GT_WX + (x0 - b.x0);
-        const float* g0 = img + (size_t)ch * ihw + (ptrdiff_t)y0 * w + x0;
-        if (b.fits) {
-          if (xin0 && yin0) vnw = sw[so];
-          if (xin1 && yin0) vne = sw[so + 1];
-          if (xin0 && yin1) vsw = sw[so + GT_WX];
-          if (xin1 && yin1) vse = sw[so + GT_WX + 1];
-        } else {
-          if (xin0 && yin0) vnw = __ldg(g0);
-          if (xin1 && yin0) vne = __ldg(g0 + 1);
-          if (xin0 && yin1) vsw = __ldg(g0 + w);
-          if (xin1 && yin1) vse = __ldg(g0 + w + 1);
-        }
-        const float gg = go[p];
-        // grad_grid: ATen's kernel term by term
-        gix[p] -= vnw * (y1 - t[p].iy) * gg;
-        giy[p] -= vnw * (x1 - t[p].ix) * gg;
-        gix[p] += vne * (y1 - t[p].iy) * gg;
-        giy[p] -= vne * (t[p].ix - fx) * gg;
-        gix[p] -= vsw * (t[p].iy - fy) * gg;
-        giy[p] += vsw * (x1 - t[p].ix) * gg;
-        gix[p] += vse * (t[p].iy - fy) * gg;
-        giy[p] += vse * (t[p].ix - fx) * gg;
-        if (wants) {
-          const float cnw = t[p].nw * gg, cne = t[p].ne * gg, csw = t[p].sw * gg, cse = t[p].se * gg;
-          if (b.fits) {
-            if (xin0 && yin0) atomicAdd(sa + so, cnw);
-            if (xin1 && yin0) atomicAdd(sa + so + 1, cne);
-            if (xin0 && yin1) atomicAdd(sa + so + GT_WX, csw);
-            if (xin1 && yin1) atomicAdd(sa + so + GT_WX + 1, cse);
-          } else {
-            float* dp = dimg + (size_t)nn * C * ihw + (size_t)ch * ihw + (ptrdiff_t)y0 * w + x0;
-            if (xin0 && yin0) atomicAdd(dp, cnw);
-            if (xin1 && yin0) atomicAdd(dp + 1, cne);
-            if (xin0 && yin1) atomicAdd(dp + w, csw);
-            if (xin1 && yin1) atomicAdd(dp + w + 1, cse);
-          }
-        }
-      }
-    }
-  }
-  {
-    float* dg = dgrid + gidx * 2;
-    const float sx = (float)w / 2.f, sy = (float)h / 2.f;     // ATen: grad multipliers size/2 for align_corners=False
-    if (act[1] && ((((uintptr_t)dg) & 15) == 0)) *reinterpret_cast<float4*>(dg) = make_float4(sx * gix[0], sy * giy[0], sx * gix[1], sy * giy[1]);
-    else {
-      if (act[0]) { dg[0] = sx * gix[0]; dg[1] = sy * giy[0]; }
-      if (act[1]) { dg[2] = sx * gix[1]; dg[3] = sy * giy[1]; }
-    }
-  }
-  if (NG > 0 && b.fits) {
-    __syncthreads();
-    // flush: one RED per touched input pixel and channel (zeros are skipped: most of a window's margin)
-    const int rows = b.y1 - b.y0 + 1;
-    for (int i = threadIdx.x; i < NG * C * rows * GT_WX; i += GT_THREADS) {
-      const int xw = i % GT_WX;
-      int r = i / GT_WX;
-      const int yr = r % rows; r /= rows;
-      const int ch = r % C, gi = r / C;
-      const float v = sacc[((size_t)(gi * C + ch) * GT_WY + yr) * GT_WX + xw];
-      const int x = b.x0 + xw;
-      if (v != 0.f && x < w) {
-        float* dimg = (G0 && gi == 0) ? dimg0 : dimg1;
-        atomicAdd(dimg + (size_t)nn * C * ihw + (size_t)ch * ihw + (size_t)(b.y0 + yr) * w + x, v);
-      }
-    }
-  }
-}
-
 NEMAR_API int nemar_grid_sample_fwd(const float* img0, const float* img1, int nimg, int n, int c, int h,
                                     int w, const float* grid, int ho, int wo, float* out0, float* out1,
                                     int32_t* idx_dump, void* stream) {
@@ -629,21 +346,12 @@ NEMAR_API int nemar_grid_sample_fwd(const float* img0, const float* img1, int ni
   NEMAR_REQUIRE(n > 0 && c > 0 && h > 0 && w > 0 && ho > 0 && wo > 0, "grid_sample_fwd: bad dims");
   cudaStream_t s = (cudaStream_t)stream;
   bool al16 = ((((uintptr_t)grid) | ((uintptr_t)out0) | ((uintptr_t)(nimg == 2 ? out1 : out0))) & 15) == 0;
-  static const int variant = [] { const char* e = getenv("NEMAR_GS_VARIANT"); return e ? atoi(e) : 2; }();
+  // (a shared-memory tiled variant — 32x16 output tiles, window of the taps' bounding box staged with coalesced row
+  //  loads, scatter-add accumulated in a shared window — was measured SLOWER on B200 at 1024^2: fwd 82 vs 63 us, bwd 223 vs
+  //  203 us; the neighbour-lane tap sharing below already removes half of the gathers / REDs.  Removed in round 2.)
+  static const int variant = [] { const char* e = getenv("NEMAR_GS_VARIANT"); return e ? atoi(e) : 1; }();
   const int64_t tot = (int64_t)n * ho * wo;
-  if (variant == 2 && c == 3 && !idx_dump && (((uintptr_t)grid) & 7) == 0) {
-    const int tiles_x = (wo + GT_TW - 1) / GT_TW, tiles_y = (ho + GT_TH - 1) / GT_TH;
-    const int64_t blocks = (int64_t)tiles_x * tiles_y * n;
-    NEMAR_REQUIRE(blocks < (1ll << 31), "grid_sample_fwd: too many tiles");
-    const size_t smem = sizeof(float) * (size_t)nimg * 3 * GT_WY * GT_WX + 64 * sizeof(int);
-    if (nimg == 2) {
-      static bool attr = false;
-      if (!attr) { cudaFuncSetAttribute(grid_sample_fwd_tiled_kernel<3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }
-      grid_sample_fwd_tiled_kernel<3, 2><<<(unsigned)blocks, GT_THREADS, smem, s>>>(img0, img1, n, h, w, grid, ho, wo, out0, out1, tiles_x, tiles_y);
-    } else {
-      grid_sample_fwd_tiled_kernel<3, 1><<<(unsigned)blocks, GT_THREADS, smem, s>>>(img0, img1, n, h, w, grid, ho, wo, out0, out1, tiles_x, tiles_y);
-    }
-  } else if (variant >= 1 && c == 3 && (((uintptr_t)grid) & 7) == 0 && tot < (1ll << 31) && (int64_t)h * w < (1ll << 30)) {
+  if (variant >= 1 && c == 3 && (((uintptr_t)grid) & 7) == 0 && tot < (1ll << 31) && (int64_t)h * w < (1ll << 30)) {
     const int blocks = grid_for(tot, 256, 148 * 16);   // P = 2 points per thread was measured slower (61 -> 70 us)
     if (nimg == 2)
       grid_sample_fwd_shared_kernel<3, 2, 1><<<blocks, 256, 0, s>>>(img0, img1, n, h, w, grid, ho, wo, out0, out1, idx_dump);
@@ -872,31 +580,7 @@ NEMAR_API int nemar_grid_sample_bwd(const float* img0, const float* img1, int ni
   // the kernel treats dimg as warp-uniform per image; it handles one "has dimg" flag per image by
   // running images with/without gradient in the same loop (pointer may be NULL per image).
   int64_t total = (int64_t)n * ho * wo;
-  static const int variant = [] { const char* e = getenv("NEMAR_GS_VARIANT"); return e ? atoi(e) : 2; }();
-  if (variant == 2 && c == 3 && (((uintptr_t)grid) & 7) == 0) {
-    const int tiles_x = (wo + GT_TW - 1) / GT_TW, tiles_y = (ho + GT_TH - 1) / GT_TH;
-    const int64_t blocks = (int64_t)tiles_x * tiles_y * n;
-    NEMAR_REQUIRE(blocks < (1ll << 31), "grid_sample_bwd: too many tiles");
-    cudaStream_t st = (cudaStream_t)stream;
-    const bool g0 = dimg0 != nullptr, g1 = nimg == 2 && dimg1 != nullptr;
-    const int ng = (g0 ? 1 : 0) + (g1 ? 1 : 0);
-    const size_t smem = sizeof(float) * (size_t)(nimg + ng) * 3 * GT_WY * GT_WX + 64 * sizeof(int);
-#define NEMAR_GS_BWD(NI, A, B)                                                                                              \
-  {                                                                                                                          \
-    static bool attr = false;                                                                                                \
-    if (!attr) { cudaFuncSetAttribute(grid_sample_bwd_tiled_kernel<3, NI, A, B>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); attr = true; } \
-    grid_sample_bwd_tiled_kernel<3, NI, A, B><<<(unsigned)blocks, GT_THREADS, smem, st>>>(img0, img1, n, h, w, grid, ho, wo, dout0, dout1, \
-                                                                                          dimg0, dimg1, dgrid, tiles_x, tiles_y);          \
-  }
-    if (nimg == 1) { if (g0) NEMAR_GS_BWD(1, true, false) else NEMAR_GS_BWD(1, false, false) }
-    else if (g0 && g1) NEMAR_GS_BWD(2, true, true)
-    else if (g0) NEMAR_GS_BWD(2, true, false)
-    else if (g1) NEMAR_GS_BWD(2, false, true)
-    else NEMAR_GS_BWD(2, false, false)
-#undef NEMAR_GS_BWD
-    NEMAR_LAUNCH_CHECK();
-    return 0;
-  }
+  static const int variant = [] { const char* e = getenv("NEMAR_GS_VARIANT"); return e ? atoi(e) : 1; }();
   if (variant >= 1 && c == 3 && total < (1ll << 31) && (int64_t)h * w < (1ll << 30)) {
     const int blocks = grid_for(total, 256, 148 * 16);
     if (nimg == 2)

@@ -70,9 +70,10 @@ __device__ __forceinline__ void fill_ab(const float* __restrict__ stats, int nn,
 // ---------------------------------------------------------------------------------------------
 // forward: y = act(A*x + B) (+ residual); the halo of y is written in the same pass
 // ---------------------------------------------------------------------------------------------
-template <int ACT>
-__global__ void __launch_bounds__(256, 4)
+template <int ACT, int UU>
+__global__ void __launch_bounds__(256, UU > 2 ? 3 : 4)
 fwd_kernel(TView x, const float* __restrict__ stats, int act, TView res, int has_res, TView y, int pad_mode, float inv_hw) {
+  constexpr int U = UU;
   extern __shared__ float sm[];
   const int nn = blockIdx.y, c = y.c, G = c / 8;
   float* sA = sm; float* sB = sm + c;
@@ -212,10 +213,11 @@ reduce_kernel(TView x, const float* __restrict__ stats, int act, TView dy, int p
 // ---------------------------------------------------------------------------------------------
 // backward apply: dx = A*g' + C + xhat*D;  dres (+)= fold(dy);  db += column sums of dx
 // ---------------------------------------------------------------------------------------------
-template <int ACT>
-__global__ void __launch_bounds__(256, 3)
+template <int ACT, int UU>
+__global__ void __launch_bounds__(256, UU > 2 ? 2 : 3)
 bwd_apply_kernel(TView x, const float* __restrict__ stats, int act, TView dy, int pad_mode, const float* __restrict__ red,
                  TView dx, TView dres, int has_dres, int dres_acc, float inv_hw, float* __restrict__ dbias) {
+  constexpr int U = UU;
   extern __shared__ float sm[];     // A[c] | B[c] | C[c] | D[c] | db[c]
   const int nn = blockIdx.y, c = x.c, G = c / 8;
   float* sA = sm; float* sB = sm + c; float* sC = sm + 2 * c; float* sD = sm + 3 * c; float* sdb = sm + 4 * c;
@@ -302,6 +304,10 @@ bwd_apply_kernel(TView x, const float* __restrict__ stats, int act, TView dy, in
 // blocks per sample: ~8 CTAs per SM over the whole batch, each with at least two iterations' worth of pixels
 static inline int reduce_u() {
   static const int u = [] { const char* e = getenv("NEMAR_LEAN_RED_U"); return e ? atoi(e) : 2; }();
+  return u;
+}
+static inline int stream_u() {     // pixels in flight per thread in the forward / backward-apply passes (2 or 4)
+  static const int u = [] { const char* e = getenv("NEMAR_LEAN_U"); return e ? atoi(e) : 2; }();
   return u;
 }
 // the reductions pay a fixed latency chain per CTA (zero the shared accumulators, coefficient table, shared then

@@ -34,6 +34,9 @@ class NEMARModel(BaseModel):
                             help="[engine] 1: capture optimize_parameters (forward, both backward passes, the gradient "
                                  "all-reduces and both Adam launches) in ONE CUDA graph after 3 eager steps and replay it; "
                                  "inputs are copied into static buffers by set_input")
+        parser.add_argument("--stream_overlap", type=int, default=1,
+                            help="[engine] 1 (default): the registration network's regressor runs on a second CUDA stream, "
+                                 "concurrently with netT(real_A) (forward and backward)")
         parser.add_argument("--batch_d", type=int, default=1,
                             help="[engine] 1 (default): the discriminator evaluates its (A, B_k) pairs of one phase (real / fake_TR / "
                                  "fake_RT) in ONE pass over their batch-concatenation instead of one pass each "
@@ -144,9 +147,36 @@ class NEMARModel(BaseModel):
             self.real_B = input[b].to(self.device, non_blocking=True).float().contiguous()
         self.image_paths = input.get(a + "_paths", [])
 
+    def _stn_stream(self):
+        """Second stream for the registration network (None: disabled).  netT(real_A) and the STN's regressor are
+        independent in both directions, so the STN's many small, latency-bound kernels can fill the SMs the generator's
+        convolutions leave idle (wave tails, one-CTA-per-SM tiles); autograd replays each node on its forward stream, so
+        the backward passes overlap the same way.  Works inside the captured step (fork / join become graph edges)."""
+        if self.device.type != "cuda" or not getattr(self.opt, "stream_overlap", 1):
+            return None
+        s = self.__dict__.get("_stn_stream_obj")
+        if s is None:
+            s = self._stn_stream_obj = torch.cuda.Stream(self.device)
+        return s
+
+    def _join_stn_stream(self):
+        s = self.__dict__.get("_stn_stream_obj")
+        if s is not None:
+            torch.cuda.current_stream().wait_stream(s)
+
     def forward(self):
-        self.fake_B = self.netT(self.real_A)
-        warped, reg_term = self.netR(self.real_A, self.real_B, apply_on=[self.real_A, self.fake_B])
+        side = self._stn_stream() if hasattr(self.netR, "precompute") else None
+        if side is not None:
+            main = torch.cuda.current_stream()
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                pre = self.netR.precompute(self.real_A, self.real_B)
+            self.fake_B = self.netT(self.real_A)
+            main.wait_stream(side)
+            warped, reg_term = self.netR(self.real_A, self.real_B, apply_on=[self.real_A, self.fake_B], pre=pre)
+        else:
+            self.fake_B = self.netT(self.real_A)
+            warped, reg_term = self.netR(self.real_A, self.real_B, apply_on=[self.real_A, self.fake_B])
         self.stn_reg_term = reg_term
         self.registered_real_A = warped[0]
         self.fake_TR_B = self.netT(self.registered_real_A)   # registration first, then translation
@@ -205,6 +235,9 @@ class NEMARModel(BaseModel):
         self.loss_smoothness = opt.lambda_smooth * self.stn_reg_term
         loss = self.loss_L1_TR + self.loss_L1_RT + self.loss_GAN_TR + self.loss_GAN_RT + self.loss_smoothness
         loss.backward()
+        # the engine delivers parameter gradients inside its own backward calls (no AccumulateGrad node runs), so
+        # autograd's end-of-backward stream sync does not cover the STN's stream: join it before the Adam launch
+        self._join_stn_stream()
         return loss
 
     def backward_D(self):

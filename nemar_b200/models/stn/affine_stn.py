@@ -76,8 +76,12 @@ class AffineSTN(nn.Module):
         bx, by = self._base_coords(img_a.size(2), img_a.size(3), img_a.device)
         return F.AffineGridFn.apply(theta, bx, by)
 
-    def forward(self, img_a, img_b, apply_on=None):
-        dtheta, theta = self._get_theta(img_a, img_b)
+    def precompute(self, img_a, img_b):
+        """The affine regressor (independent of `apply_on`): see UnetSTN.precompute."""
+        return self._get_theta(img_a, img_b)
+
+    def forward(self, img_a, img_b, apply_on=None, pre=None):
+        dtheta, theta = pre if pre is not None else self._get_theta(img_a, img_b)
         if apply_on is None:
             apply_on = [img_a]
         warped = sample_all(lambda h, w, dev: F.AffineGridFn.apply(theta, *self._base_coords(h, w, dev)), apply_on)

@@ -103,9 +103,14 @@ class UnetSTN(nn.Module):
             return up
         return F.FlowGridFn.apply(up, self.grid_xs, self.grid_ys)
 
-    def forward(self, img_a, img_b, apply_on=None):
+    def precompute(self, img_a, img_b):
+        """Everything that does not depend on `apply_on` (the ResUnet and the sampling grid): NEMARModel runs it on a
+        second stream while the translation network processes real_A."""
         deformation, up = self._offsets(img_a, img_b)
-        grid = F.FlowGridFn.apply(up, self.grid_xs, self.grid_ys)
+        return deformation, F.FlowGridFn.apply(up, self.grid_xs, self.grid_ys)
+
+    def forward(self, img_a, img_b, apply_on=None, pre=None):
+        deformation, grid = pre if pre is not None else self.precompute(img_a, img_b)
         if apply_on is None:
             apply_on = [img_a]
         warped = sample_all(lambda h, w, dev: grid, apply_on)

@@ -3,7 +3,9 @@
  *
  * Follows the reference's call sites models/stn/affine_stn.py:128-130 and models/stn/unet_stn.py:121-129,167,
  * 173-174 into PyTorch ATen (third-party, un-vendored; torch 2.11.0 here):
- *   ATen/native/GridSampler.h:26-36   grid_sampler_unnormalize: ((coord + 1) * size - 1) / 2   (align_corners=False)
+ *   ATen/native/GridSampler.h:26-36   grid_sampler_unnormalize: ((coord + 1) * size - 1) / 2   (align_corners=False);
+ *       evaluated by ATen as ONE fused multiply-add fma(coord + 1, size / 2, -0.5) (vectorised CPU kernel; nvcc contraction
+ *       in the CUDA kernel): pinned by tests/test_grid_oracle.py at 288 x 384, where the two-rounding form is 1.4e-5 off
  *   ATen/native/GridSampler.h:205-207 within_bounds_2d; bilinear taps nw/ne/sw/se from floor(ix), floor(iy)
  *   ATen/native/AffineGridGenerator.cpp linspace(-1,1,n)*(n-1)/n base grid, grid = base @ theta^T
  * and models/stn/stn_losses.py:4-30 for the smoothness term.  Pinned by tests/test_grid_oracle.py against
@@ -45,8 +47,9 @@ API void oracle_grid_sample_fwd(const float* img, int n, int c, int h, int w, co
     for (int y = 0; y < ho; ++y)
       for (int x = 0; x < wo; ++x) {
         const float* g = grid + (((size_t)i * ho + y) * wo + x) * 2;
-        float ix = ((g[0] + 1.f) * (float)w - 1.f) / 2.f;
-        float iy = ((g[1] + 1.f) * (float)h - 1.f) / 2.f;
+        /* one fused multiply-add, as both ATen builds evaluate it (see the header note) */
+        float ix = fmaf(g[0] + 1.f, (float)w * 0.5f, -0.5f);
+        float iy = fmaf(g[1] + 1.f, (float)h * 0.5f, -0.5f);
         float fx = floorf(ix), fy = floorf(iy);
         int x0 = (int)fx, y0 = (int)fy;
         float x1 = fx + 1.f, y1 = fy + 1.f;
@@ -74,8 +77,9 @@ API void oracle_grid_sample_bwd(const float* img, int n, int c, int h, int w, co
     for (int y = 0; y < ho; ++y)
       for (int x = 0; x < wo; ++x) {
         const float* g = grid + (((size_t)i * ho + y) * wo + x) * 2;
-        float ix = ((g[0] + 1.f) * (float)w - 1.f) / 2.f;
-        float iy = ((g[1] + 1.f) * (float)h - 1.f) / 2.f;
+        /* one fused multiply-add, as both ATen builds evaluate it (see the header note) */
+        float ix = fmaf(g[0] + 1.f, (float)w * 0.5f, -0.5f);
+        float iy = fmaf(g[1] + 1.f, (float)h * 0.5f, -0.5f);
         float fx = floorf(ix), fy = floorf(iy);
         int x0 = (int)fx, y0 = (int)fy;
         float x1 = fx + 1.f, y1 = fy + 1.f;
