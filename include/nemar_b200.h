@@ -127,6 +127,16 @@ int nemar_pack_weights_multi(const nemar_pack_job* jobs_dev, const int* blocks_d
 int nemar_conv2d_fprop(const nemar_tensor* x, const void* w_packed, int w_cin_p, const float* bias,
                        const nemar_conv_geom* g, int act, const nemar_tensor* y, float* stats,
                        int use_tc, void* stream);
+/* Same, with InstanceNorm statistics produced IN THE CONVOLUTION'S EPILOGUE when the geometry allows it: the tiled
+ * tensor-core kernel writes per-tile column sums into `stats_ws` (plain stores) and a small kernel adds them up into
+ * stats[n][cout][2] (overwritten: no zeroing needed, no atomics, deterministic).  nemar_conv2d_fprop_stats_workspace
+ * returns the bytes `stats_ws` must hold, or 0 when this geometry takes the separate statistics pass (then stats must
+ * be zeroed by the caller as above and stats_ws is ignored). */
+int64_t nemar_conv2d_fprop_stats_workspace(const nemar_tensor* x, int w_cin_p, const nemar_conv_geom* g,
+                                           const nemar_tensor* y, int use_tc);
+int nemar_conv2d_fprop_ws(const nemar_tensor* x, const void* w_packed, int w_cin_p, const float* bias,
+                          const nemar_conv_geom* g, int act, const nemar_tensor* y, float* stats,
+                          float* stats_ws, int64_t stats_ws_bytes, int use_tc, void* stream);
 /* dx = conv_dgrad(dy); dx halo (if dx->pad>0) receives the raw padded-buffer gradient. */
 int nemar_conv2d_dgrad(const nemar_tensor* dy, const void* w_packed_d, int w_cout_p,
                        const nemar_conv_geom* g, const nemar_tensor* dx, int use_tc, void* stream);

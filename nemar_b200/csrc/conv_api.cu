@@ -42,17 +42,8 @@ static int expected_out(int in, const nemar_conv_geom* g, int k) {
   return (in + 2 * g->pad - k) / g->stride + 1;
 }
 
-NEMAR_API int nemar_conv2d_fprop(const nemar_tensor* x, const void* w_packed, int w_cin_p, const float* bias,
-                                 const nemar_conv_geom* g, int act, const nemar_tensor* y, float* stats,
-                                 int use_tc, void* stream) {
-  NEMAR_REQUIRE(view_ok(x) && view_ok(y) && w_packed && geom_ok(g), "conv2d_fprop: bad args");
-  NEMAR_REQUIRE(x->c >= g->cin && y->c >= g->cout && x->n == y->n && w_cin_p == x->c &&
-                    (x->dtype == y->dtype || y->dtype == NEMAR_F32),
-                "conv2d_fprop: channel/dtype mismatch (weights are packed for x->c input channels and share x's "
-                "dtype; y may be fp32)");
-  NEMAR_REQUIRE(y->pad == 0, "conv2d_fprop: output must not carry a halo");
-  cudaStream_t s = (cudaStream_t)stream;
-  GatherGeom gg;
+// geometry of the forward pass as a gather problem; false: bad arguments (error set)
+static int fprop_geom(const nemar_tensor* x, const nemar_conv_geom* g, const nemar_tensor* y, GatherGeom& gg) {
   gg.kh = g->kh; gg.kw = g->kw; gg.dst_padded = 0;
   if (!g->transposed) {
     NEMAR_REQUIRE(x->pad <= g->pad, "conv2d_fprop: input halo larger than the conv padding");
@@ -65,14 +56,44 @@ NEMAR_API int nemar_conv2d_fprop(const nemar_tensor* x, const void* w_packed, in
                   "conv2d_fprop(transposed): bad output extent");
     gg.sm = 1; gg.sd = g->stride; gg.pe = gg.pe_x = g->kh - 1 - g->pad;
   }
+  return 0;
+}
+
+NEMAR_API int64_t nemar_conv2d_fprop_stats_workspace(const nemar_tensor* x, int w_cin_p, const nemar_conv_geom* g,
+                                                     const nemar_tensor* y, int use_tc) {
+  if (!use_tc || !view_ok(x) || !view_ok(y) || !geom_ok(g) || y->pad != 0 || w_cin_p != x->c) return 0;
+  GatherGeom gg;
+  if (fprop_geom(x, g, y, gg)) return 0;
+  return tc_gather_stats_workspace(x, y, w_cin_p, gg);
+}
+
+NEMAR_API int nemar_conv2d_fprop_ws(const nemar_tensor* x, const void* w_packed, int w_cin_p, const float* bias,
+                                    const nemar_conv_geom* g, int act, const nemar_tensor* y, float* stats,
+                                    float* stats_ws, int64_t stats_ws_bytes, int use_tc, void* stream) {
+  NEMAR_REQUIRE(view_ok(x) && view_ok(y) && w_packed && geom_ok(g), "conv2d_fprop: bad args");
+  NEMAR_REQUIRE(x->c >= g->cin && y->c >= g->cout && x->n == y->n && w_cin_p == x->c &&
+                    (x->dtype == y->dtype || y->dtype == NEMAR_F32),
+                "conv2d_fprop: channel/dtype mismatch (weights are packed for x->c input channels and share x's "
+                "dtype; y may be fp32)");
+  NEMAR_REQUIRE(y->pad == 0, "conv2d_fprop: output must not carry a halo");
+  cudaStream_t s = (cudaStream_t)stream;
+  GatherGeom gg;
+  int rc = fprop_geom(x, g, y, gg);
+  if (rc) return rc;
   if (use_tc && tc_gather_supported(x, y, w_cin_p, gg))   // otherwise: CUDA-core engine (still on the GPU)
-    return tc_gather_gemm(x, y, w_packed, w_cin_p, bias, act, stats, gg, s);
-  int rc = generic_gather_gemm(x, y, w_packed, x->dtype, w_cin_p, bias, act, gg, s);
+    return tc_gather_gemm(x, y, w_packed, w_cin_p, bias, act, stats, gg, s, stats_ws, stats_ws_bytes);
+  rc = generic_gather_gemm(x, y, w_packed, x->dtype, w_cin_p, bias, act, gg, s);
   if (!rc && stats) {
     NEMAR_REQUIRE(act == NEMAR_ACT_NONE, "conv2d_fprop: stats need the pre-activation output");
     rc = nemar_instnorm_stats(y, stats, stream);
   }
   return rc;
+}
+
+NEMAR_API int nemar_conv2d_fprop(const nemar_tensor* x, const void* w_packed, int w_cin_p, const float* bias,
+                                 const nemar_conv_geom* g, int act, const nemar_tensor* y, float* stats,
+                                 int use_tc, void* stream) {
+  return nemar_conv2d_fprop_ws(x, w_packed, w_cin_p, bias, g, act, y, stats, nullptr, 0, use_tc, stream);
 }
 
 NEMAR_API int nemar_conv2d_dgrad(const nemar_tensor* dy, const void* w_packed_d, int w_cout_p,

@@ -41,7 +41,9 @@ bool tc_engine_built();
 int tc_set_option(const char* key, int value);   // -> previous value, -1: unknown key
 bool tc_gather_supported(const nemar_tensor* src, const nemar_tensor* dst, int wp_cs, const GatherGeom& gg);
 int tc_gather_gemm(const nemar_tensor* src, const nemar_tensor* dst, const void* wp, int wp_cs,
-                   const float* bias, int act, float* stats, const GatherGeom& gg, cudaStream_t s);
+                   const float* bias, int act, float* stats, const GatherGeom& gg, cudaStream_t s,
+                   float* stats_ws = nullptr, int64_t stats_ws_bytes = 0);
+int64_t tc_gather_stats_workspace(const nemar_tensor* src, const nemar_tensor* dst, int wp_cs, const GatherGeom& gg);
 bool tc_wgrad_supported(const nemar_tensor* x, const nemar_tensor* dy, int kh, int kw, int stride, int pe);
 int64_t tc_wgrad_workspace(const nemar_tensor* x, const nemar_tensor* dy, int kh, int kw, int stride, int pe);
 int tc_wgrad(const nemar_tensor* x, const nemar_tensor* dy, float* dw, int co_real, int ci_real, int kh, int kw, int stride,

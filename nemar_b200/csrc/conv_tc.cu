@@ -128,7 +128,9 @@ struct GatherParams {
   int cd;                        // destination channels
   const float* bias;
   int act;
-  float* stats;                  // optional [n][cd][2]: per-(sample, channel) sum / sum of squares of the fp32 pre-activation
+  float* stats;                  // optional [tiles of the whole problem][cd][2]: per-TILE column sums / sums of squares of
+                                 // the fp32 pre-activation (plain stores, no atomics; stats_finalize_kernel adds them up)
+  int stat_tile0;                // index of this launch's (parity class's) first tile in that buffer
   int kstagger;                  // 1: rotate each CTA's K-loop start
   int stages;                    // ring depth (<= GatherCfg::STAGES)
   int tpc;                       // destination tiles per CTA (each with its own TMEM accumulator)
@@ -159,9 +161,9 @@ __device__ __forceinline__ void warp_transpose_sum(float (&a)[32], int lane) {
 // branches per element behind a dependent global bias load: ~15 SASS instructions and ~80 stall cycles per output
 // element, measured with ncu — the round-1 epilogue cost as much as the whole K loop of a 256-channel tile), then
 // 16-byte stores of the first `ncols` columns (a multiple of 8).
-template <bool F32OUT>
+template <bool F32OUT, bool STATS>
 __device__ __forceinline__ void epi_chunk(const uint32_t (&r)[32], const float* __restrict__ sb, int act, void* dst,
-                                          int ncols, bool valid) {
+                                          int ncols, bool valid, float* sst, int lane) {
   float f[32];
 #pragma unroll
   for (int j = 0; j < 32; j += 4) {
@@ -180,6 +182,19 @@ __device__ __forceinline__ void epi_chunk(const uint32_t (&r)[32], const float* 
   } else if (act == NEMAR_ACT_TANH) {
 #pragma unroll
     for (int j = 0; j < 32; ++j) f[j] = tanhf(f[j]);
+  }
+  if constexpr (STATS) {
+    // InstanceNorm statistics of the fp32 pre-activation (act == NONE on these layers): column sums over this warp's
+    // 32 pixels by a transposing butterfly (31 shuffles per statistic), left in shared memory for the per-tile combine
+    float sv[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) sv[j] = valid ? f[j] : 0.f;
+    warp_transpose_sum(sv, lane);
+    sst[lane * 2] = sv[0];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) sv[j] = valid ? f[j] * f[j] : 0.f;
+    warp_transpose_sum(sv, lane);
+    sst[lane * 2 + 1] = sv[0];
   }
   if (!valid) return;
 #pragma unroll
@@ -203,9 +218,9 @@ __device__ __forceinline__ void epi_chunk(const uint32_t (&r)[32], const float* 
 // The whole accumulator row of one tile (NCH chunks of 32 columns starting at TMEM address `taddr`): the load of chunk
 // c + 1 is in flight while chunk c is converted and stored.  `off` = element offset of the row's first column in dst;
 // `cols` = number of real columns (multiple of 8; columns beyond it are not stored).
-template <int NCH, bool F32OUT>
+template <int NCH, bool F32OUT, bool STATS = false>
 __device__ __forceinline__ void epi_row(uint32_t taddr, const float* __restrict__ sbias, int act, void* dst, long long off,
-                                        int cols, bool valid) {
+                                        int cols, bool valid, float* sstat = nullptr, int lane = 0) {
   uint32_t ra[32], rb[32];
   tmem_ld_32x32_issue(taddr, ra);
 #pragma unroll
@@ -214,13 +229,13 @@ __device__ __forceinline__ void epi_row(uint32_t taddr, const float* __restrict_
     if (ch + 1 < NCH) tmem_ld_32x32_issue(taddr + (uint32_t)(ch + 1) * 32u, rb);
     {
       void* d = F32OUT ? (void*)((float*)dst + off + ch * 32) : (void*)((__nv_bfloat16*)dst + off + ch * 32);
-      epi_chunk<F32OUT>(ra, sbias + ch * 32, act, d, cols - ch * 32, valid);
+      epi_chunk<F32OUT, STATS>(ra, sbias + ch * 32, act, d, cols - ch * 32, valid, sstat + ch * 64, lane);
     }
     if (ch + 1 < NCH) {
       tmem_ld_wait(rb);
       if (ch + 2 < NCH) tmem_ld_32x32_issue(taddr + (uint32_t)(ch + 2) * 32u, ra);
       void* d = F32OUT ? (void*)((float*)dst + off + (ch + 1) * 32) : (void*)((__nv_bfloat16*)dst + off + (ch + 1) * 32);
-      epi_chunk<F32OUT>(rb, sbias + (ch + 1) * 32, act, d, cols - (ch + 1) * 32, valid);
+      epi_chunk<F32OUT, STATS>(rb, sbias + (ch + 1) * 32, act, d, cols - (ch + 1) * 32, valid, sstat + (ch + 1) * 64, lane);
     }
   }
 }
@@ -240,7 +255,8 @@ struct GatherCfg {
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : (STAGES_RAW < 2 ? 2 : STAGES_RAW);
   static constexpr uint32_t TX_BYTES = BM * BK * 2 + BN * BK * 2;
   static constexpr uint32_t ACC_COLS = BN < 32 ? 32 : BN;     // TMEM columns of one accumulator
-  static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + 1024 + 256 + (size_t)ACC_COLS * sizeof(float);
+  static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + 1024 + 256 + (size_t)ACC_COLS * sizeof(float) +
+                                 (size_t)4 * ACC_COLS * 2 * sizeof(float);     // bias tile + per-warp statistics staging
 };
 
 template <int BN, int BK, bool F32OUT>
@@ -256,6 +272,7 @@ tc_gather_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint64_t* tmem_full = empty_bar + Cfg::STAGES;     // one per accumulator
   uint32_t* tmem_slot = (uint32_t*)(tmem_full + MAX_TPC);
   float* sbias = (float*)(((uintptr_t)(tmem_slot + 2) + 15) & ~(uintptr_t)15);          // [ACC_COLS] bias of this CTA's channel tile
+  float* sstat = sbias + Cfg::ACC_COLS;            // [4 epilogue warps][ACC_COLS][2] statistics of the current tile
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // this CTA owns the consecutive destination tiles [t_first, t_first + t_count): one K pipeline runs through all
@@ -353,7 +370,25 @@ tc_gather_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                             (long long)(px * P.ostep + P.ox0) * P.ds_x + c0;
       mbar_wait(&tmem_full[ti], 0);
       tc_fence_after();
-      epi_row<(int)Cfg::ACC_COLS / 32, F32OUT>(acc + ((uint32_t)(q * 32) << 16), sbias, P.act, P.dst, off, cols, valid);
+      if (P.stats) {
+        epi_row<(int)Cfg::ACC_COLS / 32, F32OUT, true>(acc + ((uint32_t)(q * 32) << 16), sbias, P.act, P.dst, off, cols, valid,
+                                                       sstat + q * (int)Cfg::ACC_COLS * 2, lane);
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        // combine the four warps' column sums: one plain float2 store per channel of this tile
+        float2* gp = reinterpret_cast<float2*>(P.stats) + ((long long)(P.stat_tile0 + t_first + ti) * P.cd + c0);
+        for (int col = threadIdx.x - 64; col < cols; col += 128) {
+          float a = 0.f, b = 0.f;
+#pragma unroll
+          for (int w4 = 0; w4 < 4; ++w4) {
+            a += sstat[(w4 * (int)Cfg::ACC_COLS + col) * 2];
+            b += sstat[(w4 * (int)Cfg::ACC_COLS + col) * 2 + 1];
+          }
+          gp[col] = make_float2(a, b);
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");       // the next tile overwrites the staging area
+      } else {
+        epi_row<(int)Cfg::ACC_COLS / 32, F32OUT>(acc + ((uint32_t)(q * 32) << 16), sbias, P.act, P.dst, off, cols, valid);
+      }
     }   // tiles of this CTA
     tc_fence_before();
   }
@@ -893,6 +928,66 @@ int tc_set_option(const char* key, int value) {
   return -1;
 }
 
+// ---- InstanceNorm statistics from per-tile partials ----------------------------------------------------------------
+struct StatClasses { int nclass; int off[4]; int txy[4]; };      // per parity class: first tile, tiles per sample
+
+// stats[n][c] = sum over the tiles of sample n (all classes) of part[tile][c]; deterministic order, no atomics
+__global__ void __launch_bounds__(256)
+stats_finalize_kernel(const float2* __restrict__ part, float2* __restrict__ stats, int c, StatClasses K) {
+  const int nn = blockIdx.y;
+  for (int ch = blockIdx.x * blockDim.x + threadIdx.x; ch < c; ch += gridDim.x * blockDim.x) {
+    float a = 0.f, b = 0.f;
+    for (int k = 0; k < K.nclass; ++k) {
+      const float2* p = part + ((long long)K.off[k] + (long long)nn * K.txy[k]) * c + ch;
+      for (int j = 0; j < K.txy[k]; ++j) {
+        const float2 v = __ldg(p + (long long)j * c);
+        a += v.x; b += v.y;
+      }
+    }
+    stats[(long long)nn * c + ch] = make_float2(a, b);
+  }
+}
+
+// geometry of the destination index space of parity class `cls` (shared by the planner below and tc_gather_gemm)
+static void class_extent(const nemar_tensor& dst, const GatherGeom& gg, int cls, int& dh, int& dw) {
+  const int pyc = cls >> 1, pxc = cls & 1;
+  dh = (gg.sd == 2) ? (dst.h - pyc + 1) / 2 : dst.h;
+  dw = (gg.sd == 2) ? (dst.w - pxc + 1) / 2 : dst.w;
+}
+
+static int fused_stats_env() {
+  static const int v = [] { const char* e = getenv("NEMAR_FUSED_STATS"); return e ? atoi(e) : 1; }();
+  return v;
+}
+
+// Bytes of per-tile partial statistics the tiled gather kernel needs to produce InstanceNorm statistics in its
+// epilogue; 0: this geometry takes the separate reduction pass (tiles spanning several samples, fp32 output, the
+// CTA-pair or resident-patch kernels).
+int64_t tc_gather_stats_workspace(const nemar_tensor* src_in, const nemar_tensor* dst_in, int wp_cs, const GatherGeom& gg) {
+  if (!fused_stats_env() || !tc_gather_supported(src_in, dst_in, wp_cs, gg)) return 0;
+  nemar_tensor dst = *dst_in;
+  dst.h += 2 * dst.pad; dst.w += 2 * dst.pad; dst.pad = 0;
+  const int BK = chunk_for(src_in->c);
+  if (dst.dtype == NEMAR_F32) return 0;
+  if (pair_gather() && dst.c % PAIR_BN == 0 && BK == PAIR_BK) return 0;
+  const int BN = gather_bn(dst.c, BK, false);
+  if (BN < 32) return 0;
+  const int nclass = (gg.sd == 2) ? 4 : 1;
+  int64_t tiles = 0;
+  for (int cls = 0; cls < nclass; ++cls) {
+    int dh, dw, tw, th, tn;
+    class_extent(dst, gg, cls, dh, dw);
+    if (dh <= 0 || dw <= 0) continue;
+    pick_tile(dw, dh, dst.n, tw, th, tn, BM);
+    if (tn != 1) return 0;
+    tiles += (int64_t)((dw + tw - 1) / tw) * ((dh + th - 1) / th) * dst.n;
+  }
+  // the resident-patch kernel takes stride-1 k x k layers with <= 64 output channels: no fused statistics there
+  static const int rp3_env = [] { const char* e = getenv("NEMAR_TC_RP3"); return e ? atoi(e) : 1; }();
+  if (rp3_env && gg.sm == 1 && gg.sd == 1 && BN <= 64 && gg.kh * gg.kw >= 2) return 0;
+  return tiles * dst.c * 2 * (int64_t)sizeof(float);
+}
+
 bool tc_gather_supported(const nemar_tensor* src, const nemar_tensor* dst, int wp_cs, const GatherGeom& gg) {
   if (!tc_view_ok(src, false) || !tc_view_ok(dst, true)) return false;
   if (wp_cs != src->c) return false;
@@ -903,7 +998,7 @@ bool tc_gather_supported(const nemar_tensor* src, const nemar_tensor* dst, int w
 }
 
 int tc_gather_gemm(const nemar_tensor* src_in, const nemar_tensor* dst_in, const void* wp, int wp_cs, const float* bias,
-                   int act, float* stats, const GatherGeom& gg, cudaStream_t s) {
+                   int act, float* stats, const GatherGeom& gg, cudaStream_t s, float* stats_ws, int64_t stats_ws_bytes) {
   NEMAR_REQUIRE(tc_gather_supported(src_in, dst_in, wp_cs, gg), "tc_gather_gemm: unsupported geometry");
   // read / write padded buffers as plain images of extent (h+2p, w+2p): the effective padding `pe` already
   // accounts for the halo
@@ -922,6 +1017,12 @@ int tc_gather_gemm(const nemar_tensor* src_in, const nemar_tensor* dst_in, const
 
   const int nclass = (gg.sd == 2) ? 4 : 1;
   if (stats) NEMAR_REQUIRE(act == NEMAR_ACT_NONE, "tc_gather_gemm: statistics need the pre-activation output");
+  // statistics in the epilogue (per-tile partials in the caller's workspace) when the planner says this geometry can
+  const int64_t ws_need = stats ? tc_gather_stats_workspace(src_in, dst_in, wp_cs, gg) : 0;
+  const bool fused = stats && stats_ws && ws_need > 0 && stats_ws_bytes >= ws_need;
+  StatClasses SC;
+  SC.nclass = 0;
+  int stat_tiles = 0;
   for (int cls = 0; cls < nclass; ++cls) {
     GatherParams P;
     const int pyc = cls >> 1, pxc = cls & 1;   // destination parity of this class (sd == 2)
@@ -963,7 +1064,7 @@ int tc_gather_gemm(const nemar_tensor* src_in, const nemar_tensor* dst_in, const
     // resident-patch kernel for stride-1 k x k layers with <= 64 output channels: default since the converged-warp issue
     // fix (32 -> 32 @256^2: 75 us against 119 us tiled; 96 -> 32: 146 / 182 against 250 / 295); NEMAR_TC_RP3=0 disables
     static const int rp3_env = [] { const char* e = getenv("NEMAR_TC_RP3"); return e ? atoi(e) : 1; }();
-    if (rp3_env && !pair && gg.sm == 1 && gg.sd == 1) {
+    if (rp3_env && !pair && !fused && gg.sm == 1 && gg.sd == 1) {
       Rp3Params R;
       size_t rp_smem = 0;
       if (plan_rp3(P, taps_total, BN, BK, R, rp_smem)) {
@@ -997,6 +1098,12 @@ int tc_gather_gemm(const nemar_tensor* src_in, const nemar_tensor* dst_in, const
       default: rc = launch_gather_k<16>(tmA, tmB, P, ctiles, BK, f32, s); break;
     }
     if (rc) return rc;
+  }
+  if (fused) {
+    stats_finalize_kernel<<<dim3((unsigned)((dst.c + 255) / 256), (unsigned)dst.n), 256, 0, s>>>(
+        reinterpret_cast<const float2*>(stats_ws), reinterpret_cast<float2*>(stats), dst.c, SC);
+    NEMAR_LAUNCH_CHECK();
+    return 0;
   }
   if (stats) {
     // InstanceNorm statistics of the (L2-resident) output: separate reduction pass

@@ -229,6 +229,7 @@ class ConvCfg:
         kh, kw = (k, k) if isinstance(k, int) else (int(k[0]), int(k[1]))
         self.geom = L.ConvGeom(cin, cout, kh, kw, stride, pad, int(transposed))
         self.kh, self.kw = kh, kw
+        self.stats_ws = {}           # input shape -> bytes of per-tile statistics partials (0: separate pass)
         self.cin, self.cout, self.k, self.stride, self.pad = cin, cout, kh, stride, pad
         self.transposed, self.x_pad, self.act, self.stats = transposed, x_pad, act, stats
         self.out_f32, self.out_pad_t, self.use_tc = out_f32, out_pad_t, use_tc
@@ -362,15 +363,27 @@ class Conv2dFn(Function):
         wf, wd, bp = packed.get(weight, bias, cfg, x.dtype, cin_p, owner)
         ydt = torch.float32 if cfg.out_f32 else x.dtype
         y = torch.empty((n, ho, wo, cfg.cout_p), dtype=ydt, device=x.device)
-        stats = None
+        stats = ws = None
+        ws_bytes = 0
         if cfg.stats:
-            stats = ARENA.zeros((n, cfg.cout_p, 2), x.device)
-        # while the conv launches are being timed (bench.py's roofline pass) the InstanceNorm statistics pass is issued
-        # as its own call, so that the events around nemar_conv2d_fprop bracket the convolution kernel alone; it is the
-        # same kernel on the same buffers that nemar_conv2d_fprop launches itself when handed `stats`
+            xv, yv = view(x, cfg.x_pad), view(y)
+            key = (tuple(x.shape), cfg.x_pad)
+            ws_bytes = cfg.stats_ws.get(key)
+            if ws_bytes is None:      # can the conv's epilogue produce the statistics (per-tile partials)?
+                ws_bytes = int(L.lib().nemar_conv2d_fprop_stats_workspace(L.C.byref(xv), cin_p, L.C.byref(cfg.geom), L.C.byref(yv),
+                                                                           int(cfg.use_tc)))
+                cfg.stats_ws[key] = ws_bytes
+            if ws_bytes > 0 and not L.TIMER.on:
+                stats = torch.empty((n, cfg.cout_p, 2), dtype=torch.float32, device=x.device)     # overwritten by the finalize
+                ws = torch.empty(ws_bytes // 4, dtype=torch.float32, device=x.device)
+            else:
+                ws_bytes = 0
+                stats = ARENA.zeros((n, cfg.cout_p, 2), x.device)
+        # while the conv launches are being timed (bench.py's roofline pass) the InstanceNorm statistics come from the
+        # separate pass, issued as its own call, so that the events around the conv call bracket the convolution kernel alone
         split_stats = stats is not None and L.TIMER.on
-        call("nemar_conv2d_fprop", view(x, cfg.x_pad), vptr(wf), cin_p, fptr(bp), cfg.geom, cfg.act, view(y),
-             fptr(None if split_stats else stats), int(cfg.use_tc), stream())
+        call("nemar_conv2d_fprop_ws", view(x, cfg.x_pad), vptr(wf), cin_p, fptr(bp), cfg.geom, cfg.act, view(y),
+             fptr(None if split_stats else stats), fptr(ws), i64(ws_bytes), int(cfg.use_tc), stream())
         if split_stats:
             call("nemar_instnorm_stats", view(y), fptr(stats), stream())
         ctx.cfg, ctx.wd = cfg, wd

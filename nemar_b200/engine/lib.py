@@ -51,6 +51,7 @@ def lib():
         _lib = C.CDLL(LIB_PATH)
         _lib.nemar_last_error.restype = C.c_char_p
         _lib.nemar_conv2d_wgrad_workspace.restype = C.c_int64
+        _lib.nemar_conv2d_fprop_stats_workspace.restype = C.c_int64
     return _lib
 
 
@@ -104,7 +105,8 @@ COUNTERS = {"launches": 0}
 
 class KernelTimer:
     """CUDA-event timing of the conv launches on the launching stream (bench.py's live roofline numbers)."""
-    CONV = {"nemar_conv2d_fprop": (0, 6, 4, 8), "nemar_conv2d_dgrad": (4, 0, 3, 5), "nemar_conv2d_wgrad": (0, 1, 2, 6)}
+    CONV = {"nemar_conv2d_fprop": (0, 6, 4, 8), "nemar_conv2d_fprop_ws": (0, 6, 4, 10), "nemar_conv2d_dgrad": (4, 0, 3, 5),
+            "nemar_conv2d_wgrad": (0, 1, 2, 6)}
 
     def __init__(self):
         self.on = False
@@ -121,7 +123,7 @@ class KernelTimer:
         pix = (x.n * x.h * x.w) if g.transposed else (y.n * y.h * y.w)
         flops = 2.0 * pix * g.cin * g.cout * g.kh * g.kw
         eng = "tc" if int(args[itc]) else "generic"
-        op = name.replace("nemar_conv2d_", "")
+        op = name.replace("nemar_conv2d_", "").replace("fprop_ws", "fprop")
         return "%s[%s]" % (op, eng), "%s[%s] %d->%d k%d s%d%s @%dx%d" % (
             op, eng, g.cin, g.cout, g.kh, g.stride, "T" if g.transposed else "", y.h, y.w), flops
 
