@@ -1060,7 +1060,14 @@ int tc_gather_gemm(const nemar_tensor* src_in, const nemar_tensor* dst_in, const
     P.act = act;
     static const int stag = [] { const char* e = getenv("NEMAR_TC_STAGGER"); return e ? atoi(e) : 0; }();   // measured: no effect on B200 (not an L2 hot-spot problem)
     P.kstagger = stag;
-    P.stats = nullptr;
+    P.stats = fused ? stats_ws : nullptr;
+    P.stat_tile0 = stat_tiles;
+    if (fused) {
+      SC.off[SC.nclass] = stat_tiles;
+      SC.txy[SC.nclass] = P.tiles_x * P.tiles_y;
+      ++SC.nclass;
+      stat_tiles += P.tiles_x * P.tiles_y * P.tiles_n;
+    }
     // resident-patch kernel for stride-1 k x k layers with <= 64 output channels: default since the converged-warp issue
     // fix (32 -> 32 @256^2: 75 us against 119 us tiled; 96 -> 32: 146 / 182 against 250 / 295); NEMAR_TC_RP3=0 disables
     static const int rp3_env = [] { const char* e = getenv("NEMAR_TC_RP3"); return e ? atoi(e) : 1; }();

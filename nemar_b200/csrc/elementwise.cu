@@ -463,14 +463,14 @@ static int launch_plane_reduce(const nemar_tensor* xt, const float* stats, int a
     dim3 grid(nlean::chunks_for(hw, x.c / 8, x.n, true), x.n);
     if (nlean::reduce_u() == 4) {
       if (MODE == 0) {
-        nlean::reduce_kernel<MODE, 4, NEMAR_ACT_NONE><<<grid, 256, sizeof(float) * 4 * x.c, s>>>(x, stats, act, dy, pad_mode, inv_hw, out);
+        nlean::reduce_kernel<MODE, 4, NEMAR_ACT_NONE><<<grid, 256, sizeof(float) * 4 * x.c + 16384, s>>>(x, stats, act, dy, pad_mode, inv_hw, out);
       } else {
-        NLEAN_ACT_SWITCH(act, (nlean::reduce_kernel<MODE, 4, A><<<grid, 256, sizeof(float) * 4 * x.c, s>>>(x, stats, act, dy, pad_mode, inv_hw, out)));
+        NLEAN_ACT_SWITCH(act, (nlean::reduce_kernel<MODE, 4, A><<<grid, 256, sizeof(float) * 4 * x.c + 16384, s>>>(x, stats, act, dy, pad_mode, inv_hw, out)));
       }
     } else if (MODE == 0) {
-      nlean::reduce_kernel<MODE, 2, NEMAR_ACT_NONE><<<grid, 256, sizeof(float) * 4 * x.c, s>>>(x, stats, act, dy, pad_mode, inv_hw, out);
+      nlean::reduce_kernel<MODE, 2, NEMAR_ACT_NONE><<<grid, 256, sizeof(float) * 4 * x.c + 16384, s>>>(x, stats, act, dy, pad_mode, inv_hw, out);
     } else {
-      NLEAN_ACT_SWITCH(act, (nlean::reduce_kernel<MODE, 2, A><<<grid, 256, sizeof(float) * 4 * x.c, s>>>(x, stats, act, dy, pad_mode, inv_hw, out)));
+      NLEAN_ACT_SWITCH(act, (nlean::reduce_kernel<MODE, 2, A><<<grid, 256, sizeof(float) * 4 * x.c + 16384, s>>>(x, stats, act, dy, pad_mode, inv_hw, out)));
     }
     NEMAR_LAUNCH_CHECK();
     return 0;
@@ -822,10 +822,10 @@ NEMAR_API int nemar_norm_act_bwd_apply(const nemar_tensor* x, const float* stats
     if (db && !db_accumulate) cudaMemsetAsync(db, 0, sizeof(float) * xv.c, s);
     dim3 grid(nlean::chunks_for((int64_t)xv.h * xv.w, xv.c / 8, xv.n, false, true), xv.n);
     if (nlean::stream_u() == 4) {
-      NLEAN_ACT_SWITCH(act, (nlean::bwd_apply_kernel<A, 4><<<grid, 256, sizeof(float) * 5 * xv.c, s>>>(
+      NLEAN_ACT_SWITCH(act, (nlean::bwd_apply_kernel<A, 4><<<grid, 256, sizeof(float) * 5 * xv.c + 8192, s>>>(
           xv, stats, act, dyv, pad_mode, red, dxv, dr, dres != nullptr, dres_accumulate, inv_hw, db)));
     } else {
-      NLEAN_ACT_SWITCH(act, (nlean::bwd_apply_kernel<A, 2><<<grid, 256, sizeof(float) * 5 * xv.c, s>>>(
+      NLEAN_ACT_SWITCH(act, (nlean::bwd_apply_kernel<A, 2><<<grid, 256, sizeof(float) * 5 * xv.c + 8192, s>>>(
           xv, stats, act, dyv, pad_mode, red, dxv, dr, dres != nullptr, dres_accumulate, inv_hw, db)));
     }
     NEMAR_LAUNCH_CHECK();

@@ -144,7 +144,7 @@ fwd_kernel(TView x, const float* __restrict__ stats, int act, TView res, int has
 template <int MODE, int UU, int ACT>
 __global__ void __launch_bounds__(256, (MODE == 1 && UU > 2) ? 3 : 4)
 reduce_kernel(TView x, const float* __restrict__ stats, int act, TView dy, int pad_mode, float inv_hw, float* __restrict__ out) {
-  extern __shared__ float sm[];     // sacc[2c] | A[c] | B[c]
+  extern __shared__ float sm[];     // sacc[2c] (unused since the conflict-free combine) | A[c] | B[c] | partials[256/G][c][2]
   const int nn = blockIdx.y, c = x.c, G = c / 8;
   float* sacc = sm; float* sA = sm + 2 * c; float* sB = sm + 3 * c;
   for (int k = threadIdx.x; k < 2 * c; k += blockDim.x) sacc[k] = 0.f;
@@ -201,11 +201,26 @@ reduce_kernel(TView x, const float* __restrict__ stats, int act, TView dy, int p
       }
     }
   }
-#pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    atomicAdd(&sacc[(c0 + k) * 2], a0[k]);
-    atomicAdd(&sacc[(c0 + k) * 2 + 1], a1[k]);
+  // Block combine WITHOUT shared-memory atomics: the 256 / G threads that own the same channel group park their partial
+  // sums in [pixel lane][c][2] order (16 consecutive floats per thread: conflict-free vector stores), then 2c threads
+  // add the pixel lanes up.  (Round 1 used atomicAdd on sacc[(c0 + k) * 2]: the 32 lanes of a warp hit two banks —
+  // 16-way conflicts on 16 atomics per thread, ~30 us of a 30 us statistics pass; found with scripts/nbench.py.)
+  float* spart = sm + 4 * c;                  // [256 / G][c][2]
+  {
+    float4* d = reinterpret_cast<float4*>(spart + ((size_t)r.pl * c + c0) * 2);
+    d[0] = make_float4(a0[0], a1[0], a0[1], a1[1]);
+    d[1] = make_float4(a0[2], a1[2], a0[3], a1[3]);
+    d[2] = make_float4(a0[4], a1[4], a0[5], a1[5]);
+    d[3] = make_float4(a0[6], a1[6], a0[7], a1[7]);
   }
+  __syncthreads();
+  const int lanes = 256 / G;
+  for (int k = threadIdx.x; k < 2 * c; k += blockDim.x) {
+    float v = 0.f;
+    for (int l = 0; l < lanes; ++l) v += spart[(size_t)l * 2 * c + k];
+    atomicAdd(out + (size_t)nn * c * 2 + k, v);
+  }
+}
   __syncthreads();
   for (int k = threadIdx.x; k < 2 * c; k += blockDim.x) atomicAdd(out + (size_t)nn * c * 2 + k, sacc[k]);
 }
@@ -218,7 +233,7 @@ __global__ void __launch_bounds__(256, UU > 2 ? 2 : 3)
 bwd_apply_kernel(TView x, const float* __restrict__ stats, int act, TView dy, int pad_mode, const float* __restrict__ red,
                  TView dx, TView dres, int has_dres, int dres_acc, float inv_hw, float* __restrict__ dbias) {
   constexpr int U = UU;
-  extern __shared__ float sm[];     // A[c] | B[c] | C[c] | D[c] | db[c]
+  extern __shared__ float sm[];     // A[c] | B[c] | C[c] | D[c] | db[c] | partials[256/G][c]
   const int nn = blockIdx.y, c = x.c, G = c / 8;
   float* sA = sm; float* sB = sm + c; float* sC = sm + 2 * c; float* sD = sm + 3 * c; float* sdb = sm + 4 * c;
   fill_ab(stats, nn, c, inv_hw, sA, sB);
@@ -294,10 +309,18 @@ bwd_apply_kernel(TView x, const float* __restrict__ stats, int act, TView dy, in
     }
   }
   if (dbias) {
-#pragma unroll
-    for (int k = 0; k < 8; ++k) atomicAdd(&sdb[c0 + k], bsum[k]);
+    // same conflict-free block combine as the reductions: [pixel lane][c] partials, then c threads add the lanes up
+    float* spart = sm + 5 * c;                // [256 / G][c]
+    float4* d = reinterpret_cast<float4*>(spart + (size_t)r.pl * c + c0);
+    d[0] = make_float4(bsum[0], bsum[1], bsum[2], bsum[3]);
+    d[1] = make_float4(bsum[4], bsum[5], bsum[6], bsum[7]);
     __syncthreads();
-    for (int k = threadIdx.x; k < c; k += blockDim.x) atomicAdd(dbias + k, sdb[k]);
+    const int lanes = 256 / G;
+    for (int k = threadIdx.x; k < c; k += blockDim.x) {
+      float v = 0.f;
+      for (int l = 0; l < lanes; ++l) v += spart[(size_t)l * c + k];
+      atomicAdd(dbias + k, v);
+    }
   }
 }
 
