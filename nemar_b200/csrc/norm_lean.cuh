@@ -221,9 +221,6 @@ reduce_kernel(TView x, const float* __restrict__ stats, int act, TView dy, int p
     atomicAdd(out + (size_t)nn * c * 2 + k, v);
   }
 }
-  __syncthreads();
-  for (int k = threadIdx.x; k < 2 * c; k += blockDim.x) atomicAdd(out + (size_t)nn * c * 2 + k, sacc[k]);
-}
 
 // ---------------------------------------------------------------------------------------------
 // backward apply: dx = A*g' + C + xhat*D;  dres (+)= fold(dy);  db += column sums of dx
