@@ -11,6 +11,9 @@ class EngineConfig:
         # channels + a 1 x 1 conv (False: round 1's formulation, 5x the intermediate bytes)
         import os
         self.k7_xtaps = os.environ.get("NEMAR_K7_XTAPS", "1") != "0"
+        # weight gradients on their own stream: a conv's wgrad is needed only by the optimizer, so it leaves the critical
+        # path (dgrad chain) and fills the SMs the latency-bound passes leave idle
+        self.wgrad_stream = os.environ.get("NEMAR_WGRAD_STREAM", "1") != "0"
         self.step_dev = None         # device-resident step counter (int64[1]) read by the dropout kernels
         self.dropout_calls = 0       # dropout call sites seen since the step began (-> a distinct salt per site)
 

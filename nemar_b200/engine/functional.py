@@ -62,6 +62,28 @@ class _ZeroArena:
 
 ARENA = _ZeroArena()
 
+_WGRAD = {"stream": None, "pending": [], "used": False}
+
+
+def _wgrad_stream(device):
+    """The stream weight gradients run on (None: disabled / not a CUDA device)."""
+    from .config import CONFIG
+    if not CONFIG.wgrad_stream or device.type != "cuda":
+        return None
+    s = _WGRAD["stream"]
+    if s is None or s.device != device:
+        s = _WGRAD["stream"] = torch.cuda.Stream(device)
+    return s
+
+
+def join_wgrad_stream():
+    """Order the current stream behind every weight gradient issued so far (called before an optimizer consumes the
+    gradient bucket) and release the operands that were kept alive for them."""
+    if _WGRAD["used"]:
+        torch.cuda.current_stream().wait_stream(_WGRAD["stream"])
+        _WGRAD["used"] = False
+    _WGRAD["pending"].clear()
+
 
 def _deliver(param, grad):
     """Hand a parameter gradient over.  When the parameter already owns a gradient buffer (the optimizer's flat
@@ -414,15 +436,27 @@ class Conv2dFn(Function):
                  stream())
         if ctx.needs_input_grad[1]:
             direct = weight.is_leaf and weight.grad is not None and weight.grad.is_contiguous()
-            dw = weight.grad if direct else torch.empty(weight.shape, dtype=torch.float32, device=x.device)
             xv, gv = view(x, cfg.x_pad), view(gk)
             ws_bytes = L.lib().nemar_conv2d_wgrad_workspace(L.C.byref(xv), L.C.byref(gv), L.C.byref(cfg.geom),
                                                             int(cfg.use_tc))
-            ws = torch.empty(max(int(ws_bytes), 16), dtype=torch.uint8, device=x.device) if ws_bytes > 0 else None
-            call("nemar_conv2d_wgrad", xv, gv, cfg.geom, fptr(dw), vptr(ws), i64(ws_bytes), int(cfg.use_tc), int(direct),
-                 stream())
-            if direct:
-                dw = None
+            side = _wgrad_stream(x.device) if direct else None
+            if side is not None:
+                # off the critical path: the gradient lands in the optimizer's bucket, which only the Adam launch reads
+                # (join_wgrad_stream).  Operands stay referenced until that join: they may outlive this autograd node.
+                side.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(side):
+                    ws = torch.empty(max(int(ws_bytes), 16), dtype=torch.uint8, device=x.device) if ws_bytes > 0 else None
+                    call("nemar_conv2d_wgrad", xv, gv, cfg.geom, fptr(weight.grad), vptr(ws), i64(ws_bytes), int(cfg.use_tc), 1,
+                         stream())
+                _WGRAD["pending"].append((x, gk, ws))
+                _WGRAD["used"] = True
+            else:
+                dw = weight.grad if direct else torch.empty(weight.shape, dtype=torch.float32, device=x.device)
+                ws = torch.empty(max(int(ws_bytes), 16), dtype=torch.uint8, device=x.device) if ws_bytes > 0 else None
+                call("nemar_conv2d_wgrad", xv, gv, cfg.geom, fptr(dw), vptr(ws), i64(ws_bytes), int(cfg.use_tc), int(direct),
+                     stream())
+                if direct:
+                    dw = None
         if ctx.has_bias and ctx.needs_input_grad[2] and not cfg.defer_bias_grad:
             db = torch.empty(cfg.cout_p, dtype=torch.float32, device=x.device)
             call("nemar_bias_grad", view(g), fptr(db), stream())

@@ -46,6 +46,7 @@ class FlatAdam:
                 p.grad = self.flat_g[o:o + p.numel()].view(p.shape)
 
     def step(self):
+        F.join_wgrad_stream()          # weight gradients run on their own stream: the bucket is complete after this
         grad_scale = 1.0
         if self.grad_hook is not None:
             grad_scale = self.grad_hook(self.flat_g)
