@@ -197,20 +197,25 @@ def run_engine(args):
         # a graph replay has no place for per-kernel events: the roofline figures come from the SAME K steps launched
         # eagerly right after the timed (replayed) region — same kernels, same shapes, same stream.  (Only at N = 1: the
         # per-kernel figures do not depend on N, and a multi-rank run stays "eager warm-up, capture, replays only".)
+        from nemar_b200.engine.config import CONFIG as ENGINE_CONFIG
+        saved = (ENGINE_CONFIG.wgrad_stream, getattr(opt, "stream_overlap", 1))
         try:
             opt.cuda_graph = 0
+            # per-kernel events must bracket kernels that run ALONE: no second / third stream in this pass
+            ENGINE_CONFIG.wgrad_stream, opt.stream_overlap = False, 0
             step()
             L.TIMER.enable(args.kernel_timing)
             timed(dev_batch, args.steps, read_loss=False)
             kstats = L.TIMER.collect()
-            roofline_pass = ("a separate eager pass of the same %d steps right after the timed region (the timed region replays "
-                             "a CUDA graph, which has no place for per-kernel events)" % args.steps)
+            roofline_pass = ("a separate eager, single-stream pass of the same %d steps right after the timed region (the timed "
+                             "region replays a CUDA graph with three streams, which has no place for per-kernel events)" % args.steps)
         except Exception as e:      # noqa: BLE001 - the headline numbers above are already measured; never lose them
             sys.stderr.write("roofline pass failed: %r\n" % (e,))
             kstats = {}
         finally:
             L.TIMER.enable(False)
             opt.cuda_graph = 1
+            ENGINE_CONFIG.wgrad_stream, opt.stream_overlap = saved
 
     global_batch = args.batch * world
     value = global_batch * args.steps / (ms / 1e3)

@@ -166,25 +166,43 @@ def test_batched_discriminator_equals_separate_passes(name, precision, engine):
     pair, as the reference does (nemar_model.py:181,197,219,233,247): same losses and D / T+R gradients.  One model,
     --lr 0 (every step is then the same function of its input), the flag toggled between steps."""
     model, cfg, states, (A, B) = H.build_case(name, precision=precision, conv_engine=engine, more_flags=["--batch_d", "0", "--lr", "0"])
+    floors = FLOORS[precision]
+    if name == "c1_affine64":          # well-conditioned state (see test_cuda_graph_replay_equals_eager): tight floors
+        from tests.test_gpu_fidelity import _trained_state
+        _, T, R, Ds, A, B = _trained_state(name)
+        H.load_states(model, T, R, Ds)
+        floors = (5e-5, 5e-4, 2e-3)
     ref = _step_record(model, A, B)
     model.opt.batch_d = 1
     got = _step_record(model, A, B)
     model.opt.batch_d = 0
     ref_late = _step_record(model, A, B)
     best = ref if _rel(got[1], ref[1]) <= _rel(got[1], ref_late[1]) else ref_late
-    _assert_same_step(got, best, ref_late if best is ref else ref, FLOORS[precision], "batch_d 1 vs 0", model)
+    _assert_same_step(got, best, ref_late if best is ref else ref, floors, "batch_d 1 vs 0", model)
 
 
-@pytest.mark.parametrize("name,precision,engine", [("c1_affine64", "fp32", "generic"), ("c4_multires256", "bf16", "auto")])
-def test_cuda_graph_replay_equals_eager(name, precision, engine):
+@pytest.mark.parametrize("name,precision,engine,state", [("c1_affine64", "fp32", "generic", "trained"),
+                                                         ("c4_multires256", "bf16", "auto", "init")])
+def test_cuda_graph_replay_equals_eager(name, precision, engine, state):
     """--cuda_graph 1: steps 1-3 run eagerly, step 4 is captured and replayed, later steps replay the graph.  With
     --lr 0 every step is the same function of its input, so a replayed step must reproduce the eager step on the same
     input — including inputs the capture never saw.  Yardstick: the spread between two EAGER evaluations of the same
-    input (one before the capture, one after the replays).  That spread is not zero: the InstanceNorm reductions use
-    floating-point atomics, and the LSGAN gradient behind an InstanceNorm is what is left after its common mode
-    cancels, so rounding-level forward differences reach 1e-3 in the D weights and 1e-2 in T/R."""
+    input (one before the capture, one after the replays).
+    The fp32 case runs at the TRAINED state of tests/test_gpu_fidelity.py (oracle weights after 30 steps, structured
+    inputs): there the step is well conditioned (fp32 gradients 1e-6 from fp64 in the oracle) and the comparison is held
+    to 5e-4 (D) / 2e-3 (T+R) — at the seeded-init / white-noise state of round 1 a single ReLU-derivative flip moved the D
+    gradient by 3e-3 and the test had to be calibrated on that noise.  The bf16 case keeps the init state and its floors."""
     model, cfg, states, _ = H.build_case(name, precision=precision, conv_engine=engine, more_flags=["--cuda_graph", "1", "--lr", "0"])
-    X = [_case_inputs(name, k) for k in range(3)]
+    if state == "trained":
+        from tests.test_gpu_fidelity import _trained_state
+        _, T, R, Ds, _, _ = _trained_state(name)
+        H.load_states(model, T, R, Ds)
+        kw, batch, _ = H.CASE_FLAGS[name]
+        X = [H.structured_batch(batch, kw["height"], kw["width"], seed=5 + k) for k in range(3)]
+        floors = (5e-5, 5e-4, 2e-3)
+    else:
+        X = [_case_inputs(name, k) for k in range(3)]
+        floors = FLOORS[precision]
     early = [_step_record(model, *x) for x in X]               # eager (warm-up of the graph mode)
     replay = [_step_record(model, *x) for x in X]              # capture + replay, replay, replay
     assert model._graph_state["graph"] is not None and not model._graph_state["failed"], "the step was not captured"
@@ -193,7 +211,7 @@ def test_cuda_graph_replay_equals_eager(name, precision, engine):
     assert _rel(early[1][1], early[0][1]) > 1e-2, "different inputs must give different gradients (test self-check)"
     spread = [max(_rel(e[i], l[i]) for e, l in zip(early, late)) for i in (1, 2)]
     l_spread = max(float(np.max(np.abs(e[0] - l[0]) / (np.abs(l[0]) + 1e-3))) for e, l in zip(early, late))
-    f_loss, f_d, f_tr = FLOORS[precision]
+    f_loss, f_d, f_tr = floors
     rows, ok = [], True
     for k, what in enumerate(("the captured input", "input 1", "an input the capture never saw")):
         g, e, l = replay[k], early[k], late[k]
