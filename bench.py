@@ -242,6 +242,8 @@ def run_engine(args):
                 "traffic_note": traffic_note, "peak_source": peaks["source"] + ", sustained",
                 "timed_in": roofline_pass, "launches": st["n"], "avg_launch_ms": round(st["ms"] / max(st["n"], 1), 4),
                 "share_of_timed_kernels": round(st["ms"] / max(tot_ms, 1e-9), 4),
+                "kernel_note": "records are keyed on the kernel instance the library launched (nemar_last_conv_kernel); "
+                               "`top` lists the layer geometries it served, prefixed by the pass",
                 "by_kernel": {k: {"ms": round(v["ms"], 3), "n": v["n"],
                                   "tflops": round(v["flops"] / max(v["ms"], 1e-9) / 1e9, 2),
                                   "top": dict(sorted(((a, round(b, 3)) for a, b in v["top"].items()), key=lambda t: -t[1])[:args.top])}

@@ -52,6 +52,8 @@ typedef struct nemar_conv_geom {
 } nemar_conv_geom;
 
 const char* nemar_last_error(void);
+/* name of the kernel the most recent nemar_conv2d_* call on this thread launched ("" before the first); measurement aid */
+const char* nemar_last_conv_kernel(void);
 int nemar_version(void);
 /* 1 when the tcgen05/TMA implicit-GEMM path can take this geometry+dtype, else 0 (generic path). */
 int nemar_conv2d_tc_supported(const nemar_conv_geom* g, int dtype, int h_in, int w_in);

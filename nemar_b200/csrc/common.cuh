@@ -14,6 +14,7 @@
 // error plumbing
 // ---------------------------------------------------------------------------------------------
 void nemar_set_error(const char* fmt, ...);
+void nemar_note_conv_kernel(const char* fmt, ...);
 
 #define NEMAR_REQUIRE(cond, ...)          \
   do {                                    \

@@ -265,6 +265,7 @@ int generic_pack_multi(const nemar_pack_job* jobs_dev, const int* blocks_dev, in
 int generic_gather_gemm(const nemar_tensor* src, const nemar_tensor* dst, const void* wp, int w_dtype, int wp_cs,
                         const float* bias, int act, const GatherGeom& gg, cudaStream_t s) {
   TView sv = make_view(src), dv = make_view(dst);
+  nemar_note_conv_kernel("generic_gather_kernel");
   const int DH = gg.dst_padded ? dv.hp : dv.h, DW = gg.dst_padded ? dv.wp : dv.w;
   const int64_t M = (int64_t)dv.n * DH * DW;
   dim3 grid((unsigned)ceil_div64(M, TM), (unsigned)((dv.c + TN - 1) / TN));
@@ -276,6 +277,7 @@ int generic_gather_gemm(const nemar_tensor* src, const nemar_tensor* dst, const 
 int generic_wgrad(const nemar_tensor* x, const nemar_tensor* dy, float* dw, int kh, int kw, int stride, int pe,
                   int accumulate, cudaStream_t s) {
   TView xv = make_view(x), dv = make_view(dy);
+  nemar_note_conv_kernel("generic_wgrad_kernel");
   const int taps = kh * kw;
   if (!accumulate) cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)dv.c * xv.c * taps, s);
   const int64_t P = (int64_t)dv.n * dv.h * dv.w;

@@ -776,6 +776,7 @@ static int launch_gather_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const
   Q.tmem_cols = cols;
   dim3 grid((unsigned)((tiles + tpc - 1) / tpc), (unsigned)ctiles);
   tc_gather_kernel<BN, BK, F32OUT><<<grid, NTHREADS, smem_bytes, s>>>(tmA, tmB, Q);
+  nemar_note_conv_kernel("tc_gather_kernel<%d,%d,%s>", BN, BK, F32OUT ? "f32" : "bf16");
   NEMAR_LAUNCH_CHECK();
   return 0;
 }
@@ -828,6 +829,7 @@ static int launch_gather_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, co
   cfg.attrs = at; cfg.numAttrs = 1;
   cudaError_t e = cudaLaunchKernelEx(&cfg, tc_gather_pair_kernel, tmA, tmB, Q);
   NEMAR_REQUIRE(e == cudaSuccess, "tc_gather_pair_kernel launch failed: %s", cudaGetErrorString(e));
+  nemar_note_conv_kernel("tc_gather_pair_kernel");
   NEMAR_LAUNCH_CHECK();
   return 0;
 }
@@ -858,6 +860,7 @@ static int launch_rp3_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const Rp
   if (gx > R.tiles_total) gx = R.tiles_total;
   dim3 grid((unsigned)gx, (unsigned)ctiles);
   tc_rp3_kernel<BN, BK, F32OUT><<<grid, NTHREADS, smem_bytes, s>>>(tmA, tmB, R);
+  nemar_note_conv_kernel("tc_rp3_kernel<%d,%d,%s>", BN, BK, F32OUT ? "f32" : "bf16");
   NEMAR_LAUNCH_CHECK();
   return 0;
 }
@@ -1536,6 +1539,7 @@ static int launch_wgrad_t(const CUtensorMap& tmDY, const CUtensorMap& tmX, const
   }
   dim3 grid((unsigned)(pl.taps * pl.co_tiles * pl.ci_tiles), (unsigned)pl.splits);
   tc_wgrad_kernel<CA, CB, BN><<<grid, NTHREADS, pl.smem_bytes, s>>>(tmDY, tmX, P);
+  nemar_note_conv_kernel("tc_wgrad_kernel<%d,%d,%d>", CA, CB, BN);
   NEMAR_LAUNCH_CHECK();
   return 0;
 }
@@ -1559,6 +1563,7 @@ static int launch_wgrad_pair(const CUtensorMap& tmDY, const CUtensorMap& tmX, co
   cfg.attrs = at; cfg.numAttrs = 1;
   cudaError_t e = cudaLaunchKernelEx(&cfg, tc_wgrad_pair_kernel, tmDY, tmX, P);
   NEMAR_REQUIRE(e == cudaSuccess, "tc_wgrad_pair_kernel launch failed: %s", cudaGetErrorString(e));
+  nemar_note_conv_kernel("tc_wgrad_pair_kernel");
   NEMAR_LAUNCH_CHECK();
   return 0;
 }

@@ -6,14 +6,8 @@
 // models/stn/unet_stn.py:96,166,188-195; models/nemar_model.py:187-188.
 #include "common.cuh"
 #include "vec.cuh"
-#include "norm_fast.cuh"
 #include "norm_lean.cuh"
 #include <cstdlib>
-
-static bool norm_fast_enabled() {
-  static const int v = [] { const char* e = getenv("NEMAR_NORM_FAST"); return e ? atoi(e) : 1; }();
-  return v != 0;
-}
 
 // =============================================================================================
 // helpers
@@ -457,28 +451,21 @@ static int launch_plane_reduce(const nemar_tensor* xt, const float* stats, int a
   TView dy = dyt ? make_view(dyt) : x;
   const float inv_hw = 1.f / ((float)x.h * (float)x.w);
   const int64_t hw = (int64_t)x.h * x.w;
-  // measured (C2, ms/step, generic -> fast): backward reduce 5.80 -> 4.37; statistics 14.38 -> 14.89 (inside fprop),
-  // forward 2.71 -> 2.82, backward apply 6.96 -> 7.32 — so only the backward reduction takes the fast path
-  if ((nlean::enabled_mask() & (MODE == 0 ? 2 : 4)) && nfast::eligible(xt) && (!dyt || nfast::eligible(dyt))) {
-    dim3 grid(nlean::chunks_for(hw, x.c / 8, x.n, true), x.n);
-    if (nlean::reduce_u() == 4) {
-      if (MODE == 0) {
-        nlean::reduce_kernel<MODE, 4, NEMAR_ACT_NONE><<<grid, 256, sizeof(float) * 4 * x.c + 16384, s>>>(x, stats, act, dy, pad_mode, inv_hw, out);
-      } else {
-        NLEAN_ACT_SWITCH(act, (nlean::reduce_kernel<MODE, 4, A><<<grid, 256, sizeof(float) * 4 * x.c + 16384, s>>>(x, stats, act, dy, pad_mode, inv_hw, out)));
-      }
-    } else if (MODE == 0) {
-      nlean::reduce_kernel<MODE, 2, NEMAR_ACT_NONE><<<grid, 256, sizeof(float) * 4 * x.c + 16384, s>>>(x, stats, act, dy, pad_mode, inv_hw, out);
+  // bf16, 128-bit-accessible views: the cp.async-ring kernels (norm_lean.cuh); anything else: the generic templates
+  if (nlean::eligible(xt) && (!dyt || nlean::eligible(dyt))) {
+    const int S = nlean::pipe_stages(MODE == 0 ? 1 : 2);
+    const size_t smem = sizeof(float) * 2 * x.c + 16384 + nlean::ring_bytes(S, MODE == 1 ? 2 : 1);
+    // MODE 1 with a reflect halo walks the padded pixels of dy (see reduce_pipe_kernel)
+    const int opad = (MODE == 1 && dy.pad > 0 && pad_mode == NEMAR_PAD_REFLECT) ? dy.pad : 0;
+    const int64_t items = (int64_t)(x.h + 2 * opad) * (x.w + 2 * opad);
+    dim3 grid(nlean::pipe_chunks(items, x.c / 8, x.n, smem, MODE == 0 ? 4 : 3), x.n);
+    if (MODE == 0) {
+      nlean::allow_smem((const void*)nlean::reduce_pipe_kernel<MODE, NEMAR_ACT_NONE>, smem);
+      nlean::reduce_pipe_kernel<MODE, NEMAR_ACT_NONE><<<grid, 256, smem, s>>>(x, stats, act, dy, pad_mode, inv_hw, out, S);
     } else {
-      NLEAN_ACT_SWITCH(act, (nlean::reduce_kernel<MODE, 2, A><<<grid, 256, sizeof(float) * 4 * x.c + 16384, s>>>(x, stats, act, dy, pad_mode, inv_hw, out)));
+      NLEAN_ACT_SWITCH(act, (nlean::allow_smem((const void*)nlean::reduce_pipe_kernel<MODE, A>, smem),
+                             nlean::reduce_pipe_kernel<MODE, A><<<grid, 256, smem, s>>>(x, stats, act, dy, pad_mode, inv_hw, out, S)));
     }
-    NEMAR_LAUNCH_CHECK();
-    return 0;
-  }
-  if (MODE == 1 && norm_fast_enabled() && nfast::eligible(xt) && (!dyt || nfast::eligible(dyt))) {
-    const int G = x.c / 8;
-    dim3 grid(nfast::chunks_for(hw, G, x.n), x.n);
-    nfast::reduce_kernel<MODE><<<grid, 256, sizeof(float) * 2 * x.c, s>>>(x, stats, act, dy, pad_mode, inv_hw, out);
     NEMAR_LAUNCH_CHECK();
     return 0;
   }
@@ -648,20 +635,12 @@ NEMAR_API int nemar_norm_act_fwd(const nemar_tensor* x, const float* stats, int 
   TView xv = make_view(x), yv = make_view(y), rv = residual ? make_view(residual) : xv;
   const float inv_hw = 1.f / ((float)xv.h * (float)xv.w);
   cudaStream_t s = (cudaStream_t)stream;
-  if ((nlean::enabled_mask() & 1) && nfast::eligible(x) && nfast::eligible(y) && (!residual || nfast::eligible(residual))) {
-    dim3 grid(nlean::chunks_for((int64_t)yv.hp * yv.wp, yv.c / 8, yv.n), yv.n);
-    if (nlean::stream_u() == 4) {
-      NLEAN_ACT_SWITCH(act, (nlean::fwd_kernel<A, 4><<<grid, 256, sizeof(float) * 2 * yv.c, s>>>(xv, stats, act, rv, residual != nullptr, yv, pad_mode, inv_hw)));
-    } else {
-      NLEAN_ACT_SWITCH(act, (nlean::fwd_kernel<A, 2><<<grid, 256, sizeof(float) * 2 * yv.c, s>>>(xv, stats, act, rv, residual != nullptr, yv, pad_mode, inv_hw)));
-    }
-    NEMAR_LAUNCH_CHECK();
-    return 0;
-  }
-  static const bool fast_fwd = [] { const char* e = getenv("NEMAR_NORM_FAST_ALL"); return e && atoi(e); }();
-  if (fast_fwd && nfast::eligible(x) && nfast::eligible(y) && (!residual || nfast::eligible(residual))) {
-    dim3 grid(nfast::chunks_for((int64_t)yv.hp * yv.wp, yv.c / 8, yv.n), yv.n);
-    nfast::fwd_kernel<<<grid, 256, 0, s>>>(xv, stats, act, rv, residual != nullptr, yv, pad_mode, inv_hw);
+  if (nlean::eligible(x) && nlean::eligible(y) && (!residual || nlean::eligible(residual))) {
+    const int S = nlean::pipe_stages(0);
+    const size_t smem = sizeof(float) * 2 * yv.c + nlean::ring_bytes(S, residual ? 2 : 1);
+    dim3 grid(nlean::pipe_chunks((int64_t)yv.hp * yv.wp, yv.c / 8, yv.n, smem, 4), yv.n);
+    NLEAN_ACT_SWITCH(act, (nlean::allow_smem((const void*)nlean::fwd_pipe_kernel<A>, smem),
+                           nlean::fwd_pipe_kernel<A><<<grid, 256, smem, s>>>(xv, stats, act, rv, residual != nullptr, yv, pad_mode, inv_hw, S)));
     NEMAR_LAUNCH_CHECK();
     return 0;
   }
@@ -818,25 +797,14 @@ NEMAR_API int nemar_norm_act_bwd_apply(const nemar_tensor* x, const float* stats
   TView xv = make_view(x), dyv = make_view(dy), dxv = make_view(dx), dr = dres ? make_view(dres) : xv;
   const float inv_hw = 1.f / ((float)xv.h * (float)xv.w);
   cudaStream_t s = (cudaStream_t)stream;
-  if ((nlean::enabled_mask() & 8) && nfast::eligible(x) && nfast::eligible(dy) && nfast::eligible(dx) && (!dres || nfast::eligible(dres))) {
+  if (nlean::eligible(x) && nlean::eligible(dy) && nlean::eligible(dx) && (!dres || nlean::eligible(dres))) {
     if (db && !db_accumulate) cudaMemsetAsync(db, 0, sizeof(float) * xv.c, s);
-    dim3 grid(nlean::chunks_for((int64_t)xv.h * xv.w, xv.c / 8, xv.n, false, true), xv.n);
-    if (nlean::stream_u() == 4) {
-      NLEAN_ACT_SWITCH(act, (nlean::bwd_apply_kernel<A, 4><<<grid, 256, sizeof(float) * 5 * xv.c + 8192, s>>>(
-          xv, stats, act, dyv, pad_mode, red, dxv, dr, dres != nullptr, dres_accumulate, inv_hw, db)));
-    } else {
-      NLEAN_ACT_SWITCH(act, (nlean::bwd_apply_kernel<A, 2><<<grid, 256, sizeof(float) * 5 * xv.c + 8192, s>>>(
-          xv, stats, act, dyv, pad_mode, red, dxv, dr, dres != nullptr, dres_accumulate, inv_hw, db)));
-    }
-    NEMAR_LAUNCH_CHECK();
-    return 0;
-  }
-  static const bool fast_apply = [] { const char* e = getenv("NEMAR_NORM_FAST_ALL"); return e && atoi(e); }();
-  if (fast_apply && nfast::eligible(x) && nfast::eligible(dy) && nfast::eligible(dx) && (!dres || nfast::eligible(dres))) {
-    if (db && !db_accumulate) cudaMemsetAsync(db, 0, sizeof(float) * xv.c, s);
-    dim3 grid(nfast::chunks_for((int64_t)xv.h * xv.w, xv.c / 8, xv.n), xv.n);
-    nfast::bwd_apply_kernel<<<grid, 256, sizeof(float) * xv.c, s>>>(xv, stats, act, dyv, pad_mode, red, dxv, dr,
-                                                                     dres != nullptr, dres_accumulate, inv_hw, db);
+    const int S = nlean::pipe_stages(3);
+    const size_t smem = sizeof(float) * 4 * xv.c + 8192 + nlean::ring_bytes(S, (dres && dres_accumulate) ? 3 : 2);
+    dim3 grid(nlean::pipe_chunks((int64_t)xv.h * xv.w, xv.c / 8, xv.n, smem, 2), xv.n);
+    NLEAN_ACT_SWITCH(act, (nlean::allow_smem((const void*)nlean::bwd_apply_pipe_kernel<A>, smem),
+                           nlean::bwd_apply_pipe_kernel<A><<<grid, 256, smem, s>>>(
+                               xv, stats, act, dyv, pad_mode, red, dxv, dr, dres != nullptr, dres_accumulate, inv_hw, db, S)));
     NEMAR_LAUNCH_CHECK();
     return 0;
   }

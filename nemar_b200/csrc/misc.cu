@@ -14,6 +14,16 @@ void nemar_set_error(const char* fmt, ...) {
   va_end(ap);
 }
 NEMAR_API const char* nemar_last_error(void) { return g_err; }
+// name of the kernel the most recent convolution call on this thread launched (measurement aid: bench.py keys its
+// per-kernel timings on it, so that "the dominant kernel" is a kernel instance and not an op class)
+static thread_local char g_conv_kernel[96] = "";
+void nemar_note_conv_kernel(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_conv_kernel, sizeof(g_conv_kernel), fmt, ap);
+  va_end(ap);
+}
+NEMAR_API const char* nemar_last_conv_kernel(void) { return g_conv_kernel; }
 NEMAR_API int nemar_version(void) { return 100; }
 
 // ---------------------------------------------------------------------------------------------

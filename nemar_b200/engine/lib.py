@@ -50,6 +50,7 @@ def lib():
                               "g.build()'` — the engine has no CPU fallback" % LIB_PATH)
         _lib = C.CDLL(LIB_PATH)
         _lib.nemar_last_error.restype = C.c_char_p
+        _lib.nemar_last_conv_kernel.restype = C.c_char_p
         _lib.nemar_conv2d_wgrad_workspace.restype = C.c_int64
         _lib.nemar_conv2d_fprop_stats_workspace.restype = C.c_int64
     return _lib
@@ -124,8 +125,8 @@ class KernelTimer:
         flops = 2.0 * pix * g.cin * g.cout * g.kh * g.kw
         eng = "tc" if int(args[itc]) else "generic"
         op = name.replace("nemar_conv2d_", "").replace("fprop_ws", "fprop")
-        return "%s[%s]" % (op, eng), "%s[%s] %d->%d k%d s%d%s @%dx%d" % (
-            op, eng, g.cin, g.cout, g.kh, g.stride, "T" if g.transposed else "", y.h, y.w), flops
+        return "%s[%s]" % (op, eng), "%s %d->%d k%d s%d%s @%dx%d" % (
+            op, g.cin, g.cout, g.kh, g.stride, "T" if g.transposed else "", y.h, y.w), flops
 
     def collect(self):
         """-> {kernel: {ms, n, flops, top: {geometry: ms}}} (synchronises)"""
@@ -163,6 +164,12 @@ def call(name, *args):
         e0.record()
         _call(name, *args)
         e1.record()
+        if name in KernelTimer.CONV:
+            # key the record on the kernel INSTANCE the library chose (e.g. tc_gather_kernel<256,64,bf16> serves the
+            # forward and the data-gradient passes of every 256-channel layer), not on the op class
+            kname = lib().nemar_last_conv_kernel()
+            if kname:
+                key = kname.decode()
         TIMER.records.append((key, geo, flops, e0, e1))
         return
     _call(name, *args)

@@ -68,6 +68,7 @@ def child(spec, reps):
         ms = sorted(ts)[len(ts) // 2]
         out[name] = {"us": round(ms * 1e3, 1), "gbs": round(byts[name] / (ms / 1e3) / 1e9)}
     print("NBENCH " + json.dumps(out), flush=True)
+    return out
 
 
 def main():
@@ -76,9 +77,34 @@ def main():
     ap.add_argument("--variants", nargs="*", default=[""])
     ap.add_argument("--reps", type=int, default=10)
     ap.add_argument("--child", type=str, default=None)
+    ap.add_argument("--by_variant", action="store_true", help="one process per variant (all shapes inside it)")
     args = ap.parse_args()
     if args.child is not None:
-        child(tuple(json.loads(args.child)), args.reps)
+        if args.child == "null":
+            for spec in json.loads(os.environ["NBENCH_SHAPES"]):
+                child(tuple(spec[1:]), args.reps)
+        else:
+            child(tuple(json.loads(args.child)), args.reps)
+        return
+    if args.by_variant:
+        # one process per variant, every shape inside it (a fresh interpreter costs more than the measurement)
+        for var in args.variants:
+            env = dict(os.environ)
+            for kv in var.split():
+                k, v = kv.split("=", 1)
+                env[k] = v
+            print(var or "(default)")
+            for name in args.shapes:
+                env["NBENCH_SHAPES"] = json.dumps([[name] + list(SHAPES[name]) for name in args.shapes])
+            p = subprocess.run([sys.executable, os.path.abspath(__file__), "--child", "null", "--reps", str(args.reps)],
+                               capture_output=True, text=True, timeout=300, env=env)
+            lines = [l for l in p.stdout.splitlines() if l.startswith("NBENCH ")]
+            if len(lines) != len(args.shapes):
+                print("   FAILED rc=%d %s" % (p.returncode, (p.stderr or p.stdout)[-400:].replace("\n", " | ")))
+            for name, line in zip(args.shapes, lines):
+                r = json.loads(line[7:])
+                print("   %-8s %s" % (name, "  ".join("%s %6.1f us %5d GB/s" % (k, v["us"], v["gbs"]) for k, v in r.items())))
+            sys.stdout.flush()
         return
     for name in args.shapes:
         print("%s  %s" % (name, SHAPES[name]))

@@ -161,7 +161,9 @@ def test_images_to_nhwc_and_back(prec):
 @pytest.mark.parametrize("prec", ["fp32", "bf16"])
 @pytest.mark.parametrize("act", ["none", "relu", "lrelu"])
 @pytest.mark.parametrize("c,h,w,out_pad,res", [(64, 16, 16, 1, True), (32, 9, 13, 0, False), (6, 7, 5, 3, False),
-                                               (256, 8, 8, 1, True)])
+                                               (256, 8, 8, 1, True),
+                                               # long enough for the cp.async rings to wrap several times per thread
+                                               (256, 64, 64, 1, True), (128, 31, 31, 1, False), (32, 96, 80, 0, False)])
 def test_norm_act_fwd_bwd(prec, act, c, h, w, out_pad, res):
     dt = DT[prec]
     n = 2
