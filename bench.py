@@ -246,6 +246,8 @@ def run_engine(args):
                                "`top` lists the layer geometries it served, prefixed by the pass",
                 "by_kernel": {k: {"ms": round(v["ms"], 3), "n": v["n"],
                                   "tflops": round(v["flops"] / max(v["ms"], 1e-9) / 1e9, 2),
+                                  "passes": {op: {"n": o["n"], "avg_us": round(1e3 * o["ms"] / max(o["n"], 1), 1),
+                                                  "tflops": round(o["flops"] / max(o["ms"], 1e-9) / 1e9, 1)} for op, o in v.get("ops", {}).items()},
                                   "top": dict(sorted(((a, round(b, 3)) for a, b in v["top"].items()), key=lambda t: -t[1])[:args.top])}
                               for k, v in sorted(kstats.items(), key=lambda kv: -kv[1]["ms"])}}
     if roof is None and graphed and world > 1:

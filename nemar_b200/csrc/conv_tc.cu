@@ -131,7 +131,6 @@ struct GatherParams {
   float* stats;                  // optional [tiles of the whole problem][cd][2]: per-TILE column sums / sums of squares of
                                  // the fp32 pre-activation (plain stores, no atomics; stats_finalize_kernel adds them up)
   int stat_tile0;                // index of this launch's (parity class's) first tile in that buffer
-  int kstagger;                  // 1: rotate each CTA's K-loop start
   int stages;                    // ring depth (<= GatherCfg::STAGES)
   int tpc;                       // destination tiles per CTA (each with its own TMEM accumulator)
   uint32_t tmem_cols;            // power of two >= tpc * accumulator stride
@@ -304,17 +303,14 @@ tc_gather_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (warp == 0) {
     // ===== TMA producer =====
     int stage = 0; uint32_t phase = 0;
-    // every CTA walks the K loop from a different starting step (the accumulation order is irrelevant): CTAs
-    // running concurrently then fetch DIFFERENT weight tiles instead of hammering the same L2 lines
-    int kk = P.kstagger ? (int)((blockIdx.x * 5u + blockIdx.y * 3u) % (unsigned)ksteps) : 0;
+    // (rotating each CTA's K-loop start so that concurrent CTAs fetch different weight tiles was measured: no effect)
     for (int ti = 0; ti < t_count; ++ti) {
       int t = t_first + ti;
       const int tx = t % P.tiles_x; t /= P.tiles_x;
       const int ty = t % P.tiles_y;
       const int x0 = tx * P.tw, y0 = ty * P.th, n0 = (t / P.tiles_y) * P.tn;
       for (int ks = 0; ks < ksteps; ++ks) {
-        const int tap = kk / P.kchunks, kc = kk - tap * P.kchunks;
-        if (++kk == ksteps) kk = 0;
+        const int tap = ks / P.kchunks, kc = ks - tap * P.kchunks;
         mbar_wait(&empty_bar[stage], phase ^ 1);
         if (elect_one()) {
           uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
@@ -702,15 +698,6 @@ tc_rp3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
 // (dw x dh x dn) index space: e.g. the 66x66 reflect-padded maps of the ResnetBlock dgrad fill only 52 % of 128x1
 // boxes but 94 % of 4x4x8 ones.  Narrow boxes cost a little TMA efficiency, hence the small penalty below 8 pixels.
 static void pick_tile(int dw, int dh, int dn, int& tw, int& th, int& tn, int total, bool one_sample = false) {
-  static const int legacy = [] { const char* e = getenv("NEMAR_TC_LEGACY_TILES"); return e ? atoi(e) : 0; }();
-  if (legacy) {
-    tw = 1;
-    while (tw < dw && tw < total) tw <<= 1;
-    th = 1;
-    while (th < dh && tw * th < total) th <<= 1;
-    tn = total / (tw * th);
-    return;
-  }
   double best = 1e300;
   tw = total; th = 1; tn = 1;
   for (int a = total; a >= 1; a >>= 1)
@@ -745,14 +732,7 @@ static int launch_gather_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const
   Q.tile_end = tile_end < 0 ? tiles_all : tile_end;
   const int tiles = Q.tile_end - Q.tile0;
   if (tiles <= 0) return 0;
-  // ring depth: the default fills ~96 KB (two CTAs per SM); NEMAR_TC_RING_KB trades depth for residency
-  static const int ring_kb = [] { const char* e = getenv("NEMAR_TC_RING_KB"); return e ? atoi(e) : 0; }();
-  int stages = Cfg::STAGES;
-  if (ring_kb > 0 && BN != 256) {
-    stages = (int)((uint32_t)ring_kb * 1024u / Cfg::STAGE_BYTES);
-    if (stages > Cfg::STAGES) stages = Cfg::STAGES;
-    if (stages < 2) stages = 2;
-  }
+  const int stages = Cfg::STAGES;       // ~96 KB ring (two CTAs per SM) below 256-wide tiles, ~192 KB at 256
   Q.stages = stages;
   const size_t smem_bytes = Cfg::SMEM - (size_t)(Cfg::STAGES - stages) * Cfg::STAGE_BYTES;
   int occ = (int)(233472 / (smem_bytes + 1024));
@@ -816,7 +796,7 @@ static int launch_gather_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, co
   if (occ * tpc * PAIR_BN > 512) tpc = 1;               // TMEM columns shared by the CTAs resident on one SM
   Q.tpc = tpc;
   Q.tmem_cols = (uint32_t)tpc * PAIR_BN;                // 256 or 512: powers of two
-  Q.stats = nullptr; Q.kstagger = 0;
+  Q.stats = nullptr;
   const int tiles = P.tiles_x * P.tiles_y * P.tiles_n, pairs = (tiles + 1) / 2;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(2 * ((pairs + tpc - 1) / tpc)), (unsigned)ctiles, 1);
@@ -934,19 +914,29 @@ int tc_set_option(const char* key, int value) {
 // ---- InstanceNorm statistics from per-tile partials ----------------------------------------------------------------
 struct StatClasses { int nclass; int off[4]; int txy[4]; };      // per parity class: first tile, tiles per sample
 
-// stats[n][c] = sum over the tiles of sample n (all classes) of part[tile][c]; deterministic order, no atomics
+// stats[n][c] = sum over the tiles of sample n (all classes) of part[tile][c]; fixed order, no atomics.  A block owns 32
+// channels of one sample: its 8 warps take every 8th tile (one coalesced 256-byte row of float2 per warp and tile: the
+// pass is a chain of dependent L2 round trips, so the tiles are spread over the warps) and are added up in warp order.
 __global__ void __launch_bounds__(256)
 stats_finalize_kernel(const float2* __restrict__ part, float2* __restrict__ stats, int c, StatClasses K) {
-  const int nn = blockIdx.y;
-  for (int ch = blockIdx.x * blockDim.x + threadIdx.x; ch < c; ch += gridDim.x * blockDim.x) {
-    float a = 0.f, b = 0.f;
+  __shared__ float2 sp[8][32];
+  const int nn = blockIdx.y, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int ch = blockIdx.x * 32 + lane;
+  float a = 0.f, b = 0.f;
+  if (ch < c) {
     for (int k = 0; k < K.nclass; ++k) {
       const float2* p = part + ((long long)K.off[k] + (long long)nn * K.txy[k]) * c + ch;
-      for (int j = 0; j < K.txy[k]; ++j) {
+      for (int j = w; j < K.txy[k]; j += 8) {
         const float2 v = __ldg(p + (long long)j * c);
         a += v.x; b += v.y;
       }
     }
+  }
+  sp[w][lane] = make_float2(a, b);
+  __syncthreads();
+  if (w == 0 && ch < c) {
+#pragma unroll
+    for (int k = 1; k < 8; ++k) { a += sp[k][lane].x; b += sp[k][lane].y; }
     stats[(long long)nn * c + ch] = make_float2(a, b);
   }
 }
@@ -1061,8 +1051,6 @@ int tc_gather_gemm(const nemar_tensor* src_in, const nemar_tensor* dst_in, const
     P.cd = dst.c;
     P.bias = bias;
     P.act = act;
-    static const int stag = [] { const char* e = getenv("NEMAR_TC_STAGGER"); return e ? atoi(e) : 0; }();   // measured: no effect on B200 (not an L2 hot-spot problem)
-    P.kstagger = stag;
     P.stats = fused ? stats_ws : nullptr;
     P.stat_tile0 = stat_tiles;
     if (fused) {
@@ -1110,7 +1098,7 @@ int tc_gather_gemm(const nemar_tensor* src_in, const nemar_tensor* dst_in, const
     if (rc) return rc;
   }
   if (fused) {
-    stats_finalize_kernel<<<dim3((unsigned)((dst.c + 255) / 256), (unsigned)dst.n), 256, 0, s>>>(
+    stats_finalize_kernel<<<dim3((unsigned)((dst.c + 31) / 32), (unsigned)dst.n), 256, 0, s>>>(
         reinterpret_cast<const float2*>(stats_ws), reinterpret_cast<float2*>(stats), dst.c, SC);
     NEMAR_LAUNCH_CHECK();
     return 0;
@@ -1488,7 +1476,12 @@ static bool plan_wgrad(const nemar_tensor* x, const nemar_tensor* dy, int kh, in
     p.bar_offset = (uint32_t)p.stages * WGP_STAGE_BYTES;
     p.smem_bytes = (uint32_t)wgrad_pair_smem_bytes(p.stages);
     int occ = (int)(233472 / (p.smem_bytes + 1024));
+    // ONE CTA per SM (half the K splits, half the partial-sum traffic): the kernel alone is within 5 % either way, but
+    // it runs on the weight-gradient stream beside the data-gradient chain and the step is 0.7-0.9 ms shorter this way
+    // (24.9 -> 24.0-24.2 ms; a 96 KB ring also leaves the SM room for the main stream's CTAs).  NEMAR_WG_PAIR_OCC=2: two.
+    static const int occ_pair = [] { const char* e = getenv("NEMAR_WG_PAIR_OCC"); return e ? atoi(e) : 1; }();
     p.occupancy = occ < 1 ? 1 : (occ > 2 ? 2 : occ);        // 256 TMEM columns per CTA
+    if (occ_pair >= 1 && p.occupancy > occ_pair) p.occupancy = occ_pair;
     int splits = (sm_count() * p.occupancy) / base;
     if (splits > total / 8) splits = total / 8;
     if (splits > total) splits = total;
@@ -1518,9 +1511,8 @@ static bool plan_wgrad(const nemar_tensor* x, const nemar_tensor* dy, int kh, in
   p.bar_offset = (uint32_t)p.stages * p.stage_bytes + slack;
   p.smem_bytes = p.bar_offset + 1024 + 256;
   // split K so that the grid is (at most) ONE full wave of resident CTAs: a partial extra wave costs a whole one
-  static const int legacy = [] { const char* e = getenv("NEMAR_WG_LEGACY_SPLITS"); return e ? atoi(e) : 0; }();
-  int splits = legacy ? (148 * 2 + base - 1) / base : (sm_count() * occ) / base;
-  if (!legacy && splits > total / 8) splits = total / 8;     // >= 8 k-steps per CTA
+  int splits = (sm_count() * occ) / base;
+  if (splits > total / 8) splits = total / 8;     // >= 8 k-steps per CTA
   if (splits > total) splits = total;
   if (splits < 1) splits = 1;
   p.tiles_per_split = (total + splits - 1) / splits;

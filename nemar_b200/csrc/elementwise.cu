@@ -800,7 +800,8 @@ NEMAR_API int nemar_norm_act_bwd_apply(const nemar_tensor* x, const float* stats
   if (nlean::eligible(x) && nlean::eligible(dy) && nlean::eligible(dx) && (!dres || nlean::eligible(dres))) {
     if (db && !db_accumulate) cudaMemsetAsync(db, 0, sizeof(float) * xv.c, s);
     const int S = nlean::pipe_stages(3);
-    const size_t smem = sizeof(float) * 4 * xv.c + 8192 + nlean::ring_bytes(S, (dres && dres_accumulate) ? 3 : 2);
+    const int ring_nt = ((dres && dres_accumulate) ? 3 : 2) + ((dyv.pad > 0 && pad_mode == NEMAR_PAD_REFLECT) ? 1 : 0);
+    const size_t smem = sizeof(float) * 4 * xv.c + 8192 + nlean::ring_bytes(S, ring_nt);
     dim3 grid(nlean::pipe_chunks((int64_t)xv.h * xv.w, xv.c / 8, xv.n, smem, 2), xv.n);
     NLEAN_ACT_SWITCH(act, (nlean::allow_smem((const void*)nlean::bwd_apply_pipe_kernel<A>, smem),
                            nlean::bwd_apply_pipe_kernel<A><<<grid, 256, smem, s>>>(

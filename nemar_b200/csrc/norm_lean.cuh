@@ -44,19 +44,31 @@ __device__ __forceinline__ bool near_border(int y, int x, int h, int w, int p) {
   return !(y > p && y < h - 1 - p && x > p && x < w - 1 - p);
 }
 
-// gradient of the padded buffer folded onto interior pixel (y,x): main tap given, mirrored taps added when needed
-__device__ __forceinline__ void fold_extra(const TView& d, int nn, int y, int x, int c0, float (&g)[8]) {
+// gradient of the padded buffer folded onto interior pixel (y,x): main tap given, mirrored taps added when needed.
+// `first` (optional): the FIRST mirrored tap in this enumeration order, already fetched (first_mirror() names it).
+__device__ __forceinline__ void fold_extra(const TView& d, int nn, int y, int x, int c0, float (&g)[8], const uint4* first = nullptr) {
   int ys[3], xs[3];
   const int ny = reflect_sources(y, d.h, d.pad, ys);
   const int nx = reflect_sources(x, d.w, d.pad, xs);
+  int idx = 0;
   for (int a = 0; a < ny; ++a)
     for (int b = 0; b < nx; ++b) {
       if (a == 0 && b == 0) continue;   // (ys[0], xs[0]) is the main tap, already loaded
       float t[8];
-      unpack8(ldraw((const __nv_bfloat16*)d.ptr + d.pix_p(nn, ys[a], xs[b]) + c0), t);
+      unpack8((first && idx == 0) ? *first : ldraw((const __nv_bfloat16*)d.ptr + d.pix_p(nn, ys[a], xs[b]) + c0), t);
+      ++idx;
 #pragma unroll
       for (int k = 0; k < 8; ++k) g[k] += t[k];
     }
+}
+// padded coordinates of the first mirrored tap of interior pixel (y,x) in fold_extra's order; false: there is none
+__device__ __forceinline__ bool first_mirror(const TView& d, int y, int x, int& yp, int& xp) {
+  int ys[3], xs[3];
+  const int ny = reflect_sources(y, d.h, d.pad, ys);
+  const int nx = reflect_sources(x, d.w, d.pad, xs);
+  if (nx > 1) { yp = ys[0]; xp = xs[1]; return true; }
+  if (ny > 1) { yp = ys[1]; xp = xs[0]; return true; }
+  return false;
 }
 
 struct Range { uint32_t lo, hi, ppi; int cg, pl; };
@@ -337,7 +349,11 @@ bwd_apply_pipe_kernel(TView x, const float* __restrict__ stats, int act, TView d
   extern __shared__ float sm[];     // A[c] | B[c] | C[c] | D[c] | partials[256/G][c] (8 KB) | ring[S][P][nt][256] x 16 B
   const int nn = blockIdx.y, c = x.c, G = c / 8;
   const bool racc = has_dres && dres_acc;
-  const int nt = racc ? 3 : 2;
+  const bool fold = dy.pad > 0 && pad_mode == NEMAR_PAD_REFLECT;
+  // ring entries per pixel: x, dy, [old dres], [first mirrored tap of dy: border pixels fetch it through the ring too —
+  // loaded synchronously, it made the CTAs that own the border rows the stragglers of the launch]
+  const int ne = racc ? 3 : 2;
+  const int nt = ne + (fold ? 1 : 0);
   float* sA = sm; float* sB = sm + c; float* sC = sm + 2 * c; float* sD = sm + 3 * c;
   float* spart = sm + 4 * c;
   uint4* ring = reinterpret_cast<uint4*>(sm + 4 * c + 2048) + threadIdx.x;
@@ -347,7 +363,6 @@ bwd_apply_pipe_kernel(TView x, const float* __restrict__ stats, int act, TView d
   const __nv_bfloat16* db = sample_base(dy, nn, c0);
   __nv_bfloat16* ob = const_cast<__nv_bfloat16*>(sample_base(dx, nn, c0));
   __nv_bfloat16* rb = const_cast<__nv_bfloat16*>(sample_base(dres, nn, c0));
-  const bool fold = dy.pad > 0 && pad_mode == NEMAR_PAD_REFLECT;
   const uint32_t uw = (uint32_t)x.w;
   const float inv_w = 1.f / (float)x.w;
   const uint32_t first = r.lo + r.pl, step = P * r.ppi;
@@ -363,6 +378,9 @@ bwd_apply_pipe_kernel(TView x, const float* __restrict__ stats, int act, TView d
         cp_async16(dst, xb + off_in(x, yy, xx));
         cp_async16(dst + 256, db + off_in(dy, yy, xx));
         if (racc) cp_async16(dst + 512, rb + off_in(dres, yy, xx));
+        int yp, xp;
+        if (fold && near_border(yy, xx, dy.h, dy.w, dy.pad) && first_mirror(dy, yy, xx, yp, xp))
+          cp_async16(dst + ne * 256, db + off_pad(dy, yp, xp));
       }
     }
     cp_async_commit();
@@ -396,7 +414,7 @@ bwd_apply_pipe_kernel(TView x, const float* __restrict__ stats, int act, TView d
       const uint4* src = ring + ((slot * P + k) * nt) * 256;
       float g[8], v[8];
       unpack8(src[256], g);
-      if (fold && near_border(yy, xx, dy.h, dy.w, dy.pad)) fold_extra(dy, nn, yy, xx, c0, g);
+      if (fold && near_border(yy, xx, dy.h, dy.w, dy.pad)) fold_extra(dy, nn, yy, xx, c0, g, src + ne * 256);
       if (has_dres) {
         float t[8];
         if (racc) {

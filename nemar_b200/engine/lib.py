@@ -129,18 +129,22 @@ class KernelTimer:
             op, g.cin, g.cout, g.kh, g.stride, "T" if g.transposed else "", y.h, y.w), flops
 
     def collect(self):
-        """-> {kernel: {ms, n, flops, top: {geometry: ms}}} (synchronises)"""
+        """-> {kernel: {ms, n, flops, top: {geometry: ms}, ops: {pass: {ms, n, flops}}}} (synchronises)"""
         if not self.records:
             return {}
         torch.cuda.synchronize()
         out = {}
         for key, geo, flops, e0, e1 in self.records:
             ms = e0.elapsed_time(e1)
-            d = out.setdefault(key, {"ms": 0.0, "n": 0, "flops": 0.0, "top": {}})
+            d = out.setdefault(key, {"ms": 0.0, "n": 0, "flops": 0.0, "top": {}, "ops": {}})
             d["ms"] += ms
             d["n"] += 1
             d["flops"] += flops
             d["top"][geo] = d["top"].get(geo, 0.0) + ms
+            o = d["ops"].setdefault(geo.split(" ")[0], {"ms": 0.0, "n": 0, "flops": 0.0})      # the pass: fprop / dgrad / wgrad
+            o["ms"] += ms
+            o["n"] += 1
+            o["flops"] += flops
         self.records = []
         return out
 

@@ -71,10 +71,11 @@ def child(spec, reps):
         dy = torch.ones_like(y)
         flush.zero_()
         y.backward(dy)
-        for key, d in L.TIMER.collect().items():
-            o = out.setdefault(key.split("[")[0], {"ms": 0.0, "n": 0, "flops": d["flops"] / max(d["n"], 1)})
-            o["ms"] += d["ms"]
-            o["n"] += d["n"]
+        for d in L.TIMER.collect().values():       # records are keyed on the kernel instance; regroup by pass
+            for op, po in d["ops"].items():
+                o = out.setdefault(op, {"ms": 0.0, "n": 0, "flops": po["flops"] / max(po["n"], 1)})
+                o["ms"] += po["ms"]
+                o["n"] += po["n"]
     L.TIMER.enable(0)
     pix_out = y.shape[0] * y.shape[1] * y.shape[2]
     pix_in = xe.shape[0] * xe.shape[1] * xe.shape[2]
