@@ -299,13 +299,13 @@ def run_engine(args):
 
 def dominant_kernel_traffic():
     """dram__bytes_read + dram__bytes_write per launch of the dominant conv instance (256->256 k3) from the committed
-    `ncu --set full` summary — only when that capture was taken on the kernel sources this library was built from
-    (digest of nemar_b200/csrc, written by nemar_b200/build.py); otherwise null."""
+    `ncu --set full` summary — only when that capture was taken on the conv-engine sources this library was built from
+    (digest of conv_tc.cu and its headers, written at build time by nemar_b200/build.py); otherwise null."""
     try:
         prof = json.load(open(os.path.join(ROOT, "profiles", "dominant_kernel_ncu.json")))
-        built = open(os.path.join(ROOT, "nemar_b200", "build", "stamp")).read().strip()
-        if prof.get("lib_digest") != built:
-            return None, "no ncu capture of this build (profiles/dominant_kernel_ncu.json was taken on digest %s...)" % str(prof.get("lib_digest"))[:12]
+        built = open(os.path.join(ROOT, "nemar_b200", "build", "stamp_conv_tc")).read().strip()
+        if prof.get("conv_tc_digest") != built:
+            return None, "no ncu capture of this build's conv engine (profiles/dominant_kernel_ncu.json was taken on digest %s...)" % str(prof.get("conv_tc_digest"))[:12]
         pl = prof["per_launch"]
         return (round((pl["dram__bytes_read_MB"] + pl["dram__bytes_write_MB"]) * 1e6),
                 "dram bytes/launch of the 256->256 k3 fprop instance from %s (algorithmic 70.3 MB: the bf16 output stays in "

@@ -34,6 +34,15 @@ def _digest(paths):
     return h.hexdigest()
 
 
+# the translation unit of the tensor-core conv engine and everything it includes: profiles/dominant_kernel_ncu.json is a
+# capture of ITS dominant kernel, and bench.py reports `roofline.traffic` from that file only while this digest matches
+CONV_TC_UNIT = ["conv_tc.cu", "tc_common.cuh", "conv_internal.cuh", "common.cuh"]
+
+
+def conv_tc_digest():
+    return _digest([os.path.join(CSRC, f) for f in CONV_TC_UNIT] + [os.path.join(HERE, "..", "include", "nemar_b200.h")])
+
+
 def build(force=False, verbose=True):
     os.makedirs(OBJ, exist_ok=True)
     headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
@@ -42,6 +51,9 @@ def build(force=False, verbose=True):
     stamp = os.path.join(OBJ, "stamp")
     dig = _digest(srcs + headers)
     if not force and os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read() == dig:
+        if not os.path.exists(os.path.join(OBJ, "stamp_conv_tc")):
+            with open(os.path.join(OBJ, "stamp_conv_tc"), "w") as f:
+                f.write(conv_tc_digest())
         return LIB
     nvcc = _nvcc()
 
@@ -64,6 +76,8 @@ def build(force=False, verbose=True):
         raise RuntimeError("link failed:\n%s\n%s" % (r.stdout, r.stderr))
     with open(stamp, "w") as f:
         f.write(dig)
+    with open(os.path.join(OBJ, "stamp_conv_tc"), "w") as f:
+        f.write(conv_tc_digest())
     if verbose:
         print("built", LIB)
     return LIB

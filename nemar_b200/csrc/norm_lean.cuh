@@ -129,6 +129,12 @@ __device__ __forceinline__ void fill_ab(const float* __restrict__ stats, int nn,
   }
 }
 
+// a thread's 8 coefficients of one table into registers (the thread owns ONE channel group for all its pixels)
+__device__ __forceinline__ void coef8(const float* t, int c0, float (&r)[8]) {
+  const float4 lo = *reinterpret_cast<const float4*>(t + c0), hi = *reinterpret_cast<const float4*>(t + c0 + 4);
+  r[0] = lo.x; r[1] = lo.y; r[2] = lo.z; r[3] = lo.w; r[4] = hi.x; r[5] = hi.y; r[6] = hi.z; r[7] = hi.w;
+}
+
 // ---------------------------------------------------------------------------------------------
 // per-thread cp.async rings
 // ---------------------------------------------------------------------------------------------
@@ -201,9 +207,12 @@ reduce_pipe_kernel(TView x, const float* __restrict__ stats, int act, TView dy, 
   for (int s = 0; s < S - 1; ++s) issue((uint32_t)s, s);
   if (MODE == 1) fill_ab(stats, nn, c, inv_hw, sA, sB);
   __syncthreads();
-  float a0[8], a1[8];
+  float a0[8], a1[8], cA[8], cB[8];
 #pragma unroll
-  for (int k = 0; k < 8; ++k) { a0[k] = 0.f; a1[k] = 0.f; }
+  for (int k = 0; k < 8; ++k) { a0[k] = 0.f; a1[k] = 0.f; cA[k] = 1.f; cB[k] = 0.f; }
+  // the coefficients of this thread's channel group live in REGISTERS: re-reading them from shared memory for every
+  // pixel (the cp.async asm is a memory clobber, so the compiler must) kept the L1 / shared pipe 60-78 % busy (ncu)
+  if (MODE == 1) { coef8(sA, c0, cA); coef8(sB, c0, cB); }
   int slot = 0, islot = S - 1;
   for (uint32_t it = 0; it < niter; ++it) {
     issue(it + (uint32_t)(S - 1), islot);
@@ -222,17 +231,11 @@ reduce_pipe_kernel(TView x, const float* __restrict__ stats, int act, TView dy, 
         float g[8];
         unpack8(ring[((slot * P + k) * NT + 1) * 256], g);
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const float4 a = *reinterpret_cast<const float4*>(sA + c0 + 4 * h);
-          const float4 b = *reinterpret_cast<const float4*>(sB + c0 + 4 * h);
-          const float aa[4] = {a.x, a.y, a.z, a.w}, bb[4] = {b.x, b.y, b.z, b.w};
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float xh = fmaf(v[4 * h + j], aa[j], bb[j]);
-            const float gg = g[4 * h + j] * actg<ACT>(xh, act);
-            a0[4 * h + j] += gg;
-            a1[4 * h + j] = fmaf(gg, xh, a1[4 * h + j]);
-          }
+        for (int j = 0; j < 8; ++j) {
+          const float xh = fmaf(v[j], cA[j], cB[j]);
+          const float gg = g[j] * actg<ACT>(xh, act);
+          a0[j] += gg;
+          a1[j] = fmaf(gg, xh, a1[j]);
         }
       }
     }
@@ -303,6 +306,9 @@ fwd_pipe_kernel(TView x, const float* __restrict__ stats, int act, TView res, in
   for (int s = 0; s < S - 1; ++s) issue((uint32_t)s, s);
   fill_ab(stats, nn, c, inv_hw, sA, sB);
   __syncthreads();
+  float cA[8], cB[8];
+  coef8(sA, c0, cA);
+  coef8(sB, c0, cB);
   int slot = 0, islot = S - 1;
   for (uint32_t it = 0; it < niter; ++it) {
     issue(it + (uint32_t)(S - 1), islot);
@@ -317,14 +323,7 @@ fwd_pipe_kernel(TView x, const float* __restrict__ stats, int act, TView res, in
       if (source(p, ys, xs)) {
         unpack8(ring[((slot * P + k) * nt) * 256], v);
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const float4 a = *reinterpret_cast<const float4*>(sA + c0 + 4 * h);
-          const float4 b = *reinterpret_cast<const float4*>(sB + c0 + 4 * h);
-          v[4 * h + 0] = actf<ACT>(fmaf(v[4 * h + 0], a.x, b.x), act);
-          v[4 * h + 1] = actf<ACT>(fmaf(v[4 * h + 1], a.y, b.y), act);
-          v[4 * h + 2] = actf<ACT>(fmaf(v[4 * h + 2], a.z, b.z), act);
-          v[4 * h + 3] = actf<ACT>(fmaf(v[4 * h + 3], a.w, b.w), act);
-        }
+        for (int j = 0; j < 8; ++j) v[j] = actf<ACT>(fmaf(v[j], cA[j], cB[j]), act);
         if (has_res) {
           float q[8];
           unpack8(ring[((slot * P + k) * nt + 1) * 256], q);
@@ -397,9 +396,10 @@ bwd_apply_pipe_kernel(TView x, const float* __restrict__ stats, int act, TView d
     sC[k] = cc; sD[k] = dd;
   }
   __syncthreads();
-  float bsum[8];
+  float bsum[8], cA[8], cB[8], cC[8], cD[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) bsum[k] = 0.f;
+  coef8(sA, c0, cA); coef8(sB, c0, cB); coef8(sC, c0, cC); coef8(sD, c0, cD);
   int slot = 0, islot = S - 1;
   for (uint32_t it = 0; it < niter; ++it) {
     issue(it + (uint32_t)(S - 1), islot);
@@ -429,21 +429,12 @@ bwd_apply_pipe_kernel(TView x, const float* __restrict__ stats, int act, TView d
       }
       unpack8(src[0], v);
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const float4 a = *reinterpret_cast<const float4*>(sA + c0 + 4 * h);
-        const float4 b = *reinterpret_cast<const float4*>(sB + c0 + 4 * h);
-        const float4 cc = *reinterpret_cast<const float4*>(sC + c0 + 4 * h);
-        const float4 dd = *reinterpret_cast<const float4*>(sD + c0 + 4 * h);
-        const float aa[4] = {a.x, a.y, a.z, a.w}, bb[4] = {b.x, b.y, b.z, b.w};
-        const float c4[4] = {cc.x, cc.y, cc.z, cc.w}, d4[4] = {dd.x, dd.y, dd.z, dd.w};
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float xh = fmaf(v[4 * h + j], aa[j], bb[j]);
-          const float gg = g[4 * h + j] * actg<ACT>(xh, act);
-          const float o = fmaf(gg, aa[j], fmaf(xh, d4[j], c4[j]));
-          v[4 * h + j] = o;
-          bsum[4 * h + j] += o;
-        }
+      for (int j = 0; j < 8; ++j) {
+        const float xh = fmaf(v[j], cA[j], cB[j]);
+        const float gg = g[j] * actg<ACT>(xh, act);
+        const float o = fmaf(gg, cA[j], fmaf(xh, cD[j], cC[j]));
+        v[j] = o;
+        bsum[j] += o;
       }
       *reinterpret_cast<uint4*>(ob + off_in(dx, yy, xx)) = pack8(v);
     }

@@ -48,7 +48,11 @@ def main():
            "sm__pipe_tensor_cycles_active_pct_of_peak_sustained_elapsed": avg(num, "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed"),
            "launch__registers_per_thread": dom[0].get("launch__registers_per_thread", {}).get("value"),
            "grid": dom[0].get("Grid Size")}
-    out = {"source": note, "file": "profiles/dominant_kernel_ncu.json", "lib_digest": digest,
+    sys.path.insert(0, ROOT)
+    from nemar_b200 import build as B
+    # (the capture ran on the library whose whole-source digest is `digest`; run this script before touching csrc/ so that
+    #  the conv-engine digest below describes the same sources)
+    out = {"source": note, "file": "profiles/dominant_kernel_ncu.json", "lib_digest": digest, "conv_tc_digest": B.conv_tc_digest(),
            "kernel": "tc_gather_kernel<256, 64, false>  (ResnetBlock conv 256->256 k3 on the reflect-padded 66x66 map, batch 16: 512 tiles of "
                      "128 pixels x 256 channels over 256 CTAs, two tiles per CTA)",
            "per_launch": per,
