@@ -1,7 +1,7 @@
 """InstanceNorm-pass micro-benchmark (A/B tool like scripts/kbench.py): times the statistics pass, the normalise+act
 forward, and the two backward passes through the C ABI on the C2 shapes, L2 flushed between launches.
 
-  python scripts/nbench.py --variants "" "NEMAR_LEAN_U=4 NEMAR_LEAN_RED_U=4" --shapes res256 stn32
+  python scripts/nbench.py --by_variant --variants "" "NEMAR_LEAN_PIPE=3" "NEMAR_LEAN_PIPE_APPLY=4" --shapes res256 stn32
 
 GB/s = algorithmic bytes (every operand once) / time."""
 import argparse
@@ -94,8 +94,7 @@ def main():
                 k, v = kv.split("=", 1)
                 env[k] = v
             print(var or "(default)")
-            for name in args.shapes:
-                env["NBENCH_SHAPES"] = json.dumps([[name] + list(SHAPES[name]) for name in args.shapes])
+            env["NBENCH_SHAPES"] = json.dumps([[name] + list(SHAPES[name]) for name in args.shapes])
             p = subprocess.run([sys.executable, os.path.abspath(__file__), "--child", "null", "--reps", str(args.reps)],
                                capture_output=True, text=True, timeout=300, env=env)
             lines = [l for l in p.stdout.splitlines() if l.startswith("NBENCH ")]

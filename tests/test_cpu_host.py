@@ -225,3 +225,44 @@ def test_device_prefetcher_passthrough_on_cpu():
     batches = [{"A": torch.full((2, 3, 4, 4), float(i)), "B": torch.zeros(2, 3, 4, 4), "A_paths": "a%d" % i} for i in range(3)]
     got = list(DevicePrefetcher(batches, "cpu"))
     assert [float(b["A"][0, 0, 0, 0]) for b in got] == [0.0, 1.0, 2.0] and got[1]["A_paths"] == "a1" and len(DevicePrefetcher(batches, "cpu")) == 3
+
+
+def test_roofline_traffic_is_tied_to_the_conv_engine_sources(tmp_path, monkeypatch):
+    """bench.py reports `roofline.traffic` from the committed ncu capture only while the capture's conv-engine digest equals
+    the digest the library was built from; any other digest must give null (never a number of another build)."""
+    import json
+    import bench
+    from nemar_b200 import build as B
+    root = tmp_path / "repo"
+    (root / "profiles").mkdir(parents=True)
+    (root / "nemar_b200" / "build").mkdir(parents=True)
+    dig = B.conv_tc_digest()
+    assert dig == B.conv_tc_digest() and len(dig) == 64          # a pure function of the sources and flags
+    prof = {"conv_tc_digest": dig, "file": "profiles/dominant_kernel_ncu.json",
+            "per_launch": {"dram__bytes_read_MB": 36.5, "dram__bytes_write_MB": 0.5}}
+    (root / "profiles" / "dominant_kernel_ncu.json").write_text(json.dumps(prof))
+    (root / "nemar_b200" / "build" / "stamp_conv_tc").write_text(dig)
+    monkeypatch.setattr(bench, "ROOT", str(root))
+    traffic, note = bench.dominant_kernel_traffic()
+    assert traffic == 37000000 and "256->256" in note
+    (root / "nemar_b200" / "build" / "stamp_conv_tc").write_text("0" * 64)
+    traffic, note = bench.dominant_kernel_traffic()
+    assert traffic is None and "no ncu capture" in note
+
+
+def test_launch_share_aggregation(tmp_path):
+    """scripts/launch_shares.py: per-kernel shares of an ncu launch list (units normalised, commas in kernel names kept apart)."""
+    import subprocess
+    import sys
+    rows = ['"ID","Process ID","Process Name","Host Name","Kernel Name","Context","Stream","Block Size","Grid Size","Device","CC","Section Name","Metric Name","Metric Unit","Metric Value"',
+            '"0","1","python","h","k_a(int, float)","1","7","(256, 1, 1)","(8, 1, 1)","0","10.0","Command line profiler metrics","gpu__time_duration.sum","us","30.0"',
+            '"1","1","python","h","k_b()","1","7","(256, 1, 1)","(8, 1, 1)","0","10.0","Command line profiler metrics","gpu__time_duration.sum","ns","10,000"',
+            '"2","1","python","h","k_a(int, float)","1","7","(256, 1, 1)","(8, 1, 1)","0","10.0","Command line profiler metrics","gpu__time_duration.sum","us","30.0"',
+            '"3","1","python","h","k_b()","1","7","(256, 1, 1)","(8, 1, 1)","0","10.0","Command line profiler metrics","gpu__time_duration.sum","ns","10,000"']
+    src = tmp_path / "l.csv"
+    src.write_text("==PROF== noise\n" + "\n".join(rows) + "\n")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "scripts", "launch_shares.py"), str(src), "2", "note"],
+                         capture_output=True, text=True, check=True).stdout.splitlines()
+    assert out[0] == "# note" and "2 launches and 0.04 ms" in out[1]
+    assert out[3] == "75.00,0.030,1.0,30.0,k_a(int; float)" and out[4] == "25.00,0.010,1.0,10.0,k_b()"
