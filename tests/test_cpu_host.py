@@ -266,3 +266,25 @@ def test_launch_share_aggregation(tmp_path):
                          capture_output=True, text=True, check=True).stdout.splitlines()
     assert out[0] == "# note" and "2 launches and 0.04 ms" in out[1]
     assert out[3] == "75.00,0.030,1.0,30.0,k_a(int; float)" and out[4] == "25.00,0.010,1.0,10.0,k_b()"
+
+
+def test_zero_arena_bookkeeping():
+    """engine/functional.py::_ZeroArena (host logic, device-agnostic): slices handed out within a step are disjoint and
+    zero, dirty slices are zero again after the next begin(), and outside a step zeros() falls back to torch.zeros."""
+    from nemar_b200.engine.functional import _ZeroArena
+    ar = _ZeroArena()
+    free = ar.zeros((3, 5), "cpu")                       # not inside a step: an ordinary tensor
+    assert free.shape == (3, 5) and float(free.abs().sum()) == 0.0 and ar.buf is None
+    ar.begin("cpu")
+    a, b = ar.zeros((2, 3, 2), "cpu"), ar.zeros((7,), "cpu")
+    assert a.data_ptr() != b.data_ptr() and (b.data_ptr() - a.data_ptr()) % 16 == 0 and b.data_ptr() - a.data_ptr() >= a.numel() * 4
+    a.fill_(3.0)
+    b.fill_(5.0)
+    assert float(a.sum()) == 36.0 and float(b.sum()) == 35.0      # disjoint: neither fill touched the other slice
+    big = ar.zeros((ar.buf.numel(),), "cpu")             # does not fit behind a and b: falls back, the arena stays intact
+    assert big.data_ptr() != ar.buf.data_ptr() and float(a.sum()) == 36.0
+    ar.end()
+    assert ar.zeros((4,), "cpu").data_ptr() != a.data_ptr()
+    ar.begin("cpu")
+    a2 = ar.zeros((2, 3, 2), "cpu")
+    assert a2.data_ptr() == a.data_ptr() and float(a2.abs().sum()) == 0.0 and float(ar.buf[:64].abs().sum()) == 0.0
