@@ -288,3 +288,50 @@ def test_zero_arena_bookkeeping():
     ar.begin("cpu")
     a2 = ar.zeros((2, 3, 2), "cpu")
     assert a2.data_ptr() == a.data_ptr() and float(a2.abs().sum()) == 0.0 and float(ar.buf[:64].abs().sum()) == 0.0
+
+
+def test_pack_refresh_selects_and_stamps_the_right_entries(monkeypatch):
+    """engine/functional.py::refresh_packs (host logic; the C-ABI calls are recorded, not executed): after an optimizer
+    step ONE multi-tensor launch re-packs exactly the cache entries whose parameter lives in that optimizer's flat
+    buffer — forward pack, data-gradient pack and padded bias each — and marks them current; entries of other
+    optimizers stay untouched, entries derived from a parameter by a host-side transform are invalidated instead."""
+    from nemar_b200.engine import functional as F
+    from nemar_b200.engine import lib as L
+    calls = []
+    monkeypatch.setattr(F, "call", lambda name, *a: calls.append((name, a)))
+    monkeypatch.setattr(F, "stream", lambda: None)
+    flat = torch.zeros(4096)
+    other = torch.zeros(4096)
+    w1 = flat[0:6 * 3 * 3 * 3].view(6, 3, 3, 3)           # cout 6 (padded to 16), cin 3 (padded to 16), k3
+    b1 = flat[200:206]
+    w2 = flat[1024:1024 + 16 * 16].view(16, 16, 1, 1)
+    w3 = other[0:16 * 16].view(16, 16, 1, 1)
+    cfg1 = F.ConvCfg(3, 6, 3, pad=1, cout_p=16)
+    cfg2 = F.ConvCfg(16, 16, 1)
+    p1, p2, p3, pd = F.PackedWeights(), F.PackedWeights(), F.PackedWeights(), F.PackedWeights()
+    p1.get(w1, b1, cfg1, torch.float32, 16)
+    p2.get(w2, None, cfg2, torch.float32, 16)
+    p3.get(w3, None, cfg2, torch.float32, 16)
+    pd.get(w2.clone(), None, cfg2, torch.float32, 16, owner=w2)        # e.g. a tap-transformed copy of w2
+    assert [c[0] for c in calls] == ["nemar_pack_weights"] * 4
+    e1, e2, e3, ed = (list(p.cache.values())[0] for p in (p1, p2, p3, pd))
+    assert e1["bp"] is not None and e2["bp"] is None and ed["derived"]
+    calls.clear()
+    p1.get(w1, b1, cfg1, torch.float32, 16)               # current: no re-pack
+    assert calls == []
+    stamp3 = e3["stamp"]
+    e1["stamp"] = e2["stamp"] = "stale"
+    F.refresh_packs(flat)
+    assert [c[0] for c in calls] == ["nemar_pack_weights_multi"]
+    nblocks = calls[0][1][2]
+    jobs = 3 + 2                                          # e1: forward, backward, bias; e2: forward, backward
+    per = lambda o, k, i: (o * k * i + 2047) // 2048
+    assert nblocks == 2 * per(16, 9, 16) + per(16, 1, 1) + 2 * per(16, 1, 16)
+    plan = F._PACK_PLANS[flat.data_ptr()]
+    assert plan[1].numel() == jobs * L.C.sizeof(F._PackJob) and plan[2].numel() == 2 * nblocks
+    assert e1["stamp"] == F.PackedWeights._stamp(w1, b1, None) and e2["stamp"] == F.PackedWeights._stamp(w2, None, None)
+    assert e3["stamp"] == stamp3 and ed["stamp"] is None  # other optimizer untouched; derived entry invalidated
+    calls.clear()
+    pd.get(w2.clone(), None, cfg2, torch.float32, 16, owner=w2)
+    assert [c[0] for c in calls] == ["nemar_pack_weights"]           # ... and re-packed by its next use
+    F._PACK_PLANS.pop(flat.data_ptr(), None)
