@@ -56,8 +56,8 @@ def _bucket_err(net, truth, grads=None):
 
 # bucket-norm error bounds vs the fp64 oracle at the trained state (T, R, D).  Measured on B200 (profiles/r02_fidelity_gpu.txt).
 # Measured (profiles/r02_fidelity_gpu.txt, r02_fp32_gradient_error_probes.txt): fp32 engine D 3e-6; T / R between 4e-6 / 3e-6
-# and 2.4e-3 / 8e-4 from run to run (atomics-ordered plane sums deciding blocks of activation-derivative bits on flat
-# regions: DESIGN.md section 3; not the one-pass variance, not the Adam step, not stale weight packs); bf16 engine
+# and 2.4e-3 / 8e-4 from run to run (derivative bits of the few activations within rounding of zero, ~1e-4 each:
+# DESIGN.md section 3, scripts/relu_flip_probe.py; not the one-pass variance, not the Adam step, not stale packs); bf16 engine
 # T 6e-2 / R 2.6e-2 / D 5e-2 — BELOW the reference under torch.autocast(bfloat16) on the same state (9.8e-2 / 9.6e-2 / 8.4e-2).
 BOUNDS = {"fp32": (6e-3, 3e-3, 1e-4), "bf16": (0.10, 0.06, 0.08)}
 
