@@ -4,7 +4,7 @@
 mkdir -p gpurun_out
 O=gpurun_out
 cat nemar_b200/build/stamp > $O/r2s_lib_digest.txt
-echo "== fp32 gradient error probe"; timeout -s KILL 600 python scripts/fp32_grad_error_probe.py > $O/r2s_fp32_probe.txt 2>&1; echo rc=$?; grep -E "^==|bucket" $O/r2s_fp32_probe.txt
+echo "== fp32 gradient error probe"; timeout -s KILL 600 python tests/probes/fp32_grad_error_probe.py > $O/r2s_fp32_probe.txt 2>&1; echo rc=$?; grep -E "^==|bucket" $O/r2s_fp32_probe.txt
 B="python bench.py --profile --cuda_graph 0 --steps 1 --warmup 1 --no_cpu_baseline --grid_sample_bench 0 --kernel_timing 0 --torch_gpu_reference 0 --stream_overlap 0"
 echo "== ncu --set full (norm passes)"
 NEMAR_WGRAD_STREAM=0 timeout -s KILL 400 ncu --set full --clock-control none -k regex:"bwd_apply_pipe_kernel|reduce_pipe_kernel|fwd_pipe_kernel" -s 100 -c 70 -o /tmp/r2s_norm -f $B > $O/r2s_ncu_norm.log 2>&1; echo rc=$?

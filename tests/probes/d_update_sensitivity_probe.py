@@ -2,11 +2,11 @@
 noise in the DISCRIMINATOR's gradient?  The T/R phase differentiates through the discriminator AFTER its Adam update,
 and Adam's first update is lr * g / (|g| + eps) ~ lr * sign(g): an element whose gradient is smaller than the noise moves
 by +-lr at random.  The fp32 engine is 3e-6 off on netD's gradients but 2e-3 on netT's (8e-4 netR) at the default
-learning rate, and 1e-4 / 1e-5 with lr = 0 (scripts/fp32_grad_error_probe.py).  Here the fp64 oracle's discriminator
+learning rate, and 1e-4 / 1e-5 with lr = 0 (tests/probes/fp32_grad_error_probe.py).  Here the fp64 oracle's discriminator
 gradient is perturbed before the Adam step with (a) relative and (b) absolute (RMS-scaled, per tensor) Gaussian noise
 of that size.
 
-    python scripts/d_update_sensitivity_probe.py [--noise 3e-6]
+    python tests/probes/d_update_sensitivity_probe.py [--noise 3e-6]
 """
 import argparse
 import os
@@ -15,7 +15,7 @@ from collections import OrderedDict
 
 import torch
 
-sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", ".."))
 from oracle import nemar_oracle as O  # noqa: E402
 from tests import helpers as H  # noqa: E402
 

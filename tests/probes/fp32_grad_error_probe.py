@@ -4,14 +4,14 @@ state (tests/test_gpu_fidelity.py) the fp32 ORACLE is 1e-6 from fp64 but the fp3
 (the T/R phase differentiates through the discriminator AFTER its Adam update) and once with lr = 0 on both sides
 (the discriminator stays put: no coupling through its update).
 
-    python scripts/fp32_grad_error_probe.py
+    python tests/probes/fp32_grad_error_probe.py
 """
 import os
 import sys
 
 import torch
 
-sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", ".."))
 from oracle import nemar_oracle as O  # noqa: E402
 from tests import helpers as H  # noqa: E402
 from tests.test_gpu_fidelity import _trained_state  # noqa: E402

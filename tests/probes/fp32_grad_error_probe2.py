@@ -1,19 +1,19 @@
 """GPU probe, second question: the fp32 engine's T/R gradient error appears only when the discriminator moves
-(scripts/fp32_grad_error_probe.py: 2e-3 at lr = 2e-4, 1e-4 at lr = 0).  Is the engine's UPDATED discriminator different
+(tests/probes/fp32_grad_error_probe.py: 2e-3 at lr = 2e-4, 1e-4 at lr = 0).  Is the engine's UPDATED discriminator different
 from the oracle's, or does the engine's T/R backward see a different discriminator than its forward?
   (1) per tensor: max |D'_engine - D'_oracle64| / lr;
   (2) the fp64 oracle's T/R gradients recomputed with the ENGINE's updated discriminator substituted for its own:
       if the engine then agrees to ~1e-4, the whole discrepancy is the update (Adam on rounding-level gradients);
       if not, the engine's backward through D is inconsistent with the D it evaluated.
 
-    python scripts/fp32_grad_error_probe2.py
+    python tests/probes/fp32_grad_error_probe2.py
 """
 import os
 import sys
 
 import torch
 
-sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", ".."))
 from oracle import nemar_oracle as O  # noqa: E402
 from tests import helpers as H  # noqa: E402
 from tests.test_gpu_fidelity import _trained_state  # noqa: E402

@@ -7,18 +7,18 @@ with the discriminator it holds.  Which mechanism?  One engine step per variant,
   no_batch_d  : --batch_d 0 (one discriminator pass per image pair instead of one batched pass per phase)
   no_streams  : weight gradients and the STN regressor on the main stream
 
-    python scripts/fp32_grad_error_probe3.py
+    python tests/probes/fp32_grad_error_probe3.py
 """
 import os
 import sys
 
 import torch
 
-sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", ".."))
 from oracle import nemar_oracle as O  # noqa: E402
 from tests import helpers as H  # noqa: E402
 from tests.test_gpu_fidelity import _trained_state  # noqa: E402
-from scripts.fp32_grad_error_probe2 import oracle_step, bucket  # noqa: E402
+from tests.probes.fp32_grad_error_probe2 import oracle_step, bucket  # noqa: E402
 
 
 def engine_errors(truth, T, R, Ds, A, B, flags=(), repack=False, streams=True):

@@ -1,15 +1,15 @@
 """GPU probe, fourth question: the fp32 engine's T/R gradient error against the fp64 oracle was 2.3e-3 / 8e-4 in five
 runs and 4e-6 / 3e-6 in one (probe 3's first model).  Is that run-to-run noise of the engine (atomics-ordered sums
 deciding ReLU masks on degenerate planes), or does it depend on whether the oracle or the engine ran first in the process?
-    python scripts/fp32_grad_error_probe4.py engine_first|oracle_first
+    python tests/probes/fp32_grad_error_probe4.py engine_first|oracle_first
 """
 import os
 import sys
 
-sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", ".."))
 from tests import helpers as H  # noqa: E402
 from tests.test_gpu_fidelity import _trained_state  # noqa: E402
-from scripts.fp32_grad_error_probe2 import oracle_step, bucket  # noqa: E402
+from tests.probes.fp32_grad_error_probe2 import oracle_step, bucket  # noqa: E402
 
 
 def main():

@@ -8,7 +8,7 @@ measured against the fp64 oracle, as a function of the STATE the step is evaluat
 Per state it prints, per network, the median over weight tensors of |g - g64| / |g64| for the fp32 oracle and for
 the oracle under torch.autocast(bfloat16), and the split of the T/R gradient into its L1 and adversarial parts.
 
-    python scripts/grad_fidelity_probe.py [--steps 30] [--case c1_affine64]
+    python tests/probes/grad_fidelity_probe.py [--steps 30] [--case c1_affine64]
 """
 import argparse
 import os
@@ -18,7 +18,7 @@ from collections import OrderedDict
 import numpy as np
 import torch
 
-sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", ".."))
 from oracle import nemar_oracle as O  # noqa: E402
 from tests import helpers as H  # noqa: E402
 

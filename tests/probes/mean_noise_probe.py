@@ -4,7 +4,7 @@ The engine's plane sums are atomics-ordered, so the last bits of every plane mea
 oracle's InstanceNorm gets its plane mean and variance perturbed by a relative Gaussian noise of one fp32 ulp-ish size
 (default 1e-7), several seeds, and the T / R / D weight gradients are compared with the UNPERTURBED fp32 oracle.
 
-    python scripts/mean_noise_probe.py [--noise 1e-7] [--seeds 6]
+    python tests/probes/mean_noise_probe.py [--noise 1e-7] [--seeds 6]
 """
 import argparse
 import os
@@ -13,11 +13,11 @@ from collections import OrderedDict
 
 import torch
 
-sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", ".."))
 from oracle import nemar_oracle as O  # noqa: E402
 from tests import helpers as H  # noqa: E402
-from scripts.grad_fidelity_probe import grads  # noqa: E402
-from scripts.onepass_var_probe import bucket_err  # noqa: E402
+from tests.probes.grad_fidelity_probe import grads  # noqa: E402
+from tests.probes.onepass_var_probe import bucket_err  # noqa: E402
 
 
 def main():

@@ -3,7 +3,7 @@
 Runs the fp32 oracle at the trained state twice — ATen instance_norm vs a one-pass fp32 restatement of the engine's
 statistics (sum, sum of squares, rsqrt(var + eps)) — and prints both errors against the fp64 oracle.
 
-    python scripts/onepass_var_probe.py [--steps 30]
+    python tests/probes/onepass_var_probe.py [--steps 30]
 """
 import argparse
 import os
@@ -12,10 +12,10 @@ from collections import OrderedDict
 
 import torch
 
-sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", ".."))
 from oracle import nemar_oracle as O  # noqa: E402
 from tests import helpers as H  # noqa: E402
-from scripts.grad_fidelity_probe import grads  # noqa: E402
+from tests.probes.grad_fidelity_probe import grads  # noqa: E402
 
 
 def onepass_inorm(x):

@@ -7,7 +7,7 @@ and (b) flips the derivative bit of the single ReLU / LeakyReLU input closest to
 (generator, STN and discriminator; the discriminator's passes of the T/R phase feed both netT and netR), and reports the
 change of the T / R gradient (norm-wise over weight tensors).
 
-    python scripts/relu_flip_probe.py [--steps 30]
+    python tests/probes/relu_flip_probe.py [--steps 30]
 """
 import argparse
 import os
@@ -16,10 +16,10 @@ from collections import OrderedDict
 
 import torch
 
-sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", ".."))
 from oracle import nemar_oracle as O  # noqa: E402
 from tests import helpers as H  # noqa: E402
-from scripts.onepass_var_probe import bucket_err  # noqa: E402
+from tests.probes.onepass_var_probe import bucket_err  # noqa: E402
 
 REAL_RELU = torch.nn.functional.relu
 REAL_LRELU = torch.nn.functional.leaky_relu

@@ -38,6 +38,11 @@ def test_no_cpu_fallback_in_product():
             if f.endswith(".py"):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in src.replace("no CPU fallback", ""), "%s references the oracle" % f
+    # the oracle is test infrastructure: besides tests/ only bench.py (cpu_baseline / --impl reference legs) and
+    # __graft_entry__.py (smoke's checker, build of the C oracle) may touch it — not train.py, not the developer tools
+    for rel in ["train.py"] + [os.path.join("scripts", f) for f in os.listdir(os.path.join(ROOT, "scripts")) if f.endswith(".py")]:
+        src = open(os.path.join(ROOT, rel)).read()
+        assert "import oracle" not in src and "from oracle" not in src, "%s imports the oracle" % rel
 
 
 @pytest.mark.parametrize("case", ["c1_affine64", "c4_multires256"])

@@ -2,7 +2,7 @@
 
 Round 1 compared bf16 gradients only at the seeded-init / white-noise state, where the T/R gradient is what is left
 after the LSGAN common mode cancels in every InstanceNorm: there even the fp32 oracle is 6e-3 off the fp64 oracle and
-the reference under torch.autocast(bfloat16) is ~100 % off (scripts/grad_fidelity_probe.py, profiles/r02_grad_fidelity_cpu.txt).
+the reference under torch.autocast(bfloat16) is ~100 % off (tests/probes/grad_fidelity_probe.py, profiles/r02_grad_fidelity_cpu.txt).
 That state lasts a handful of steps.  Here the step is evaluated where training actually happens:
   * `trained state` = the fp32 ORACLE's weights after 30 steps on a structured batch (smooth images, B = remapped,
     4-px-shifted A): the oracle's fp32 gradients are 1e-6 from fp64 there, the autocast reference 7-9 % (bucket norm);
@@ -57,7 +57,7 @@ def _bucket_err(net, truth, grads=None):
 # bucket-norm error bounds vs the fp64 oracle at the trained state (T, R, D).  Measured on B200 (profiles/r02_fidelity_gpu.txt).
 # Measured (profiles/r02_fidelity_gpu.txt, r02_fp32_gradient_error_probes.txt): fp32 engine D 3e-6; T / R between 4e-6 / 3e-6
 # and 2.4e-3 / 8e-4 from run to run (derivative bits of the few activations within rounding of zero, ~1e-4 each:
-# DESIGN.md section 3, scripts/relu_flip_probe.py; not the one-pass variance, not the Adam step, not stale packs); bf16 engine
+# DESIGN.md section 3, tests/probes/relu_flip_probe.py; not the one-pass variance, not the Adam step, not stale packs); bf16 engine
 # T 6e-2 / R 2.6e-2 / D 5e-2 — BELOW the reference under torch.autocast(bfloat16) on the same state (9.8e-2 / 9.6e-2 / 8.4e-2).
 BOUNDS = {"fp32": (6e-3, 3e-3, 1e-4), "bf16": (0.10, 0.06, 0.08)}
 
